@@ -1,0 +1,126 @@
+// Shared scalar helpers for the sm_100a kernels: packed-symmetric indexing, stable softplus,
+// Philox4x32-10 counter RNG.  Everything here is `__host__ __device__` so the test-only host shim
+// (tests/host_shim) can run the exact per-lane arithmetic on the CPU against the oracle.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CI_HD __host__ __device__ __forceinline__
+#else
+#define CI_HD inline
+#endif
+
+#define CI_LOG_2PI 1.8378770664093453f
+
+namespace ci {
+
+// reciprocal: MUFU.RCP (+1 Newton-free multiply) on device, IEEE divide on host.
+CI_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+
+CI_HD float softplus(float u) {
+  // log(1 + e^u), stable on both tails
+  return (u > 0.f ? u : 0.f) + log1pf(expf(-fabsf(u)));
+}
+CI_HD float sigmoid(float u) {
+  float e = expf(-fabsf(u));
+  float s = 1.0f / (1.0f + e);
+  return u >= 0.f ? s : e * s;
+}
+CI_HD float log_sigmoid(float u) {
+  return (u < 0.f ? u : 0.f) - log1pf(expf(-fabsf(u)));
+}
+
+// Packed upper-triangular index of a symmetric SxS matrix (i <= j).
+template <int S>
+CI_HD constexpr int tri(int i, int j) {
+  return i * S - (i * (i - 1)) / 2 + (j - i);
+}
+template <int S>
+CI_HD constexpr int sym(int i, int j) {
+  return i <= j ? tri<S>(i, j) : tri<S>(j, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter words: (c0, c1, c2, tag); key = 64-bit seed.
+// The oracle (oracle/sts_oracle.py::philox4x32) implements the same function bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct u32x4 {
+  uint32_t x, y, z, w;
+};
+
+CI_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  hi = __umulhi(a, b);
+  lo = a * b;
+#else
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+#endif
+}
+
+CI_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(0xD2511F53u, c0, hi0, lo0);
+    mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
+// (0,1) uniform with 24 random bits: ((x >> 8) + 0.5) * 2^-24 -- exact in fp32.
+CI_HD float u32_to_unit(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+
+struct f32x4 {
+  float x, y, z, w;
+};
+
+CI_HD f32x4 philox_uniform4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, uint64_t seed) {
+  u32x4 r = philox4x32(c0, c1, c2, tag, seed);
+  return f32x4{u32_to_unit(r.x), u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w)};
+}
+
+// Four standard normals (two Box-Muller pairs).
+CI_HD f32x4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, uint64_t seed) {
+  f32x4 u = philox_uniform4(c0, c1, c2, tag, seed);
+  float r0 = sqrtf(-2.0f * logf(u.x));
+  float r1 = sqrtf(-2.0f * logf(u.z));
+  float s0, c0f, s1, c1f;
+  const float two_pi = 6.283185307179586f;
+#if defined(__CUDA_ARCH__)
+  sincosf(two_pi * u.y, &s0, &c0f);
+  sincosf(two_pi * u.w, &s1, &c1f);
+#else
+  s0 = sinf(two_pi * u.y); c0f = cosf(two_pi * u.y);
+  s1 = sinf(two_pi * u.w); c1f = cosf(two_pi * u.w);
+#endif
+  return f32x4{r0 * c0f, r0 * s0, r1 * c1f, r1 * s1};
+}
+
+// Stream tags (counter word 3) -- keep in sync with oracle/sts_oracle.py TAG_*.
+enum : uint32_t {
+  TAG_VI_INIT = 1,
+  TAG_VI_EPS = 2,
+  TAG_VI_DRAW = 3,
+  TAG_HMC_MOM = 4,
+  TAG_HMC_ACC = 5,
+  TAG_ONESTEP = 6,
+  TAG_FORECAST = 7,
+  TAG_FORECAST_X0 = 8,
+  TAG_PICK = 9,
+};
+
+}  // namespace ci

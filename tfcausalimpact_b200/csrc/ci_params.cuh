@@ -1,0 +1,154 @@
+// Parameter block of the fixed layout: unconstrained vector u[P] -> constrained values, regression
+// weights beta, prior log-density + bijector log-det, and the matching vector-Jacobian product.
+//
+// Parameter order (tfp.sts.Sum `model.parameters`, component order from
+// /root/reference/causalimpact/model.py:295,309,316):
+//   0 observation_noise_scale      sd * softplus(u)   sqrt(V), V ~ InvGamma(16, 16 (sd_y/2)^2)   model.py:289-290
+//   1 LocalLevel/_level_scale      sd * softplus(u)   sqrt(V), V ~ InvGamma(16, 16 prior_level_sd^2) model.py:284-285
+//   [k > 0]  2 global_scale_variance (softplus, InvGamma(.5,.5)), 3 global_scale_noncentered
+//            (softplus, HalfNormal(1)), 4..4+k local_scale_variances, 4+k..4+2k
+//            local_scales_noncentered, 4+2k..4+3k weights_noncentered (identity, Normal(0,1))
+//   [S > 1]  P-1 Seasonal/_drift_scale  sd * softplus(u)  LogNormal(log(.01 sd), 3)
+// beta = wn * (lsn sqrt(lsv)) * (gsn sqrt(gsv) 0.1)   -- /root/reference/tests/test_main.py:326-339
+#pragma once
+#include "ci_core.cuh"
+
+namespace ci {
+
+// Per-series constants, struct-of-arrays on the device: sconst[field * N + n].
+enum SConstField : int {
+  SC_MEAN = 0,       // constant_offset = mean(y_pre)
+  SC_SD = 1,         // observed_stddev (ddof = 0)
+  SC_M0 = 2,         // initial level mean = y_first - mean
+  SC_P0 = 3,         // (|y0c| + sd)^2
+  SC_OBS_B = 4,      // InvGamma scale for sigma_obs^2
+  SC_LEVEL_B = 5,    // InvGamma scale for sigma_level^2
+  SC_DRIFT_MU = 6,   // log(0.01 sd)
+  SC_PRIOR_CONST = 7,  // theta-independent additive constant of log prior + log-det
+  SC_NFIELDS = 8
+};
+
+#define CI_PRIOR_A 16.0f          // kLocalLevelPriorSampleSize / 2   (model.py:39, 211-213)
+#define CI_WEIGHTS_PRIOR_SCALE 0.1f
+
+CI_HD int num_params(int k, int S) { return 2 + (k > 0 ? 2 + 3 * k : 0) + (S > 1 ? 1 : 0); }
+
+struct LaneScalars {
+  float R, ql, qd, lp0;
+};
+
+// u, beta: element stride `ld`.  sc: pointer to this series' constants with field stride `scld`.
+CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int k, int S,
+                                      const float* __restrict__ sc, long scld, float* __restrict__ beta) {
+  const float sd = sc[SC_SD * scld];
+  LaneScalars o;
+  const float u0 = u[0], u1 = u[ld];
+  const float so = sd * softplus(u0), sl = sd * softplus(u1);
+  const float so2 = so * so, sl2 = sl * sl;
+  float lp = sc[SC_PRIOR_CONST * scld];
+  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(so) - sc[SC_OBS_B * scld] / so2 + log_sigmoid(u0);
+  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(sl) - sc[SC_LEVEL_B * scld] / sl2 + log_sigmoid(u1);
+  o.R = so2;
+  o.ql = sl2;
+  o.qd = 0.f;
+  if (k > 0) {
+    const float ug = u[2 * ld], un = u[3 * ld];
+    const float gsv = softplus(ug), gsn = softplus(un);
+    lp += -1.5f * logf(gsv) - 0.5f / gsv - 0.5f * gsn * gsn + log_sigmoid(ug) + log_sigmoid(un);
+    const float G = gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE;
+    const float* ulsv = u + 4 * ld;
+    const float* ulsn = u + (long)(4 + k) * ld;
+    const float* uwn = u + (long)(4 + 2 * k) * ld;
+    for (int j = 0; j < k; ++j) {
+      const float a = ulsv[(long)j * ld], b = ulsn[(long)j * ld], wn = uwn[(long)j * ld];
+      const float lsv = softplus(a), lsn = softplus(b);
+      lp += -1.5f * logf(lsv) - 0.5f / lsv - 0.5f * lsn * lsn - 0.5f * wn * wn + log_sigmoid(a) + log_sigmoid(b);
+      beta[(long)j * ld] = wn * lsn * sqrtf(lsv) * G;
+    }
+  }
+  if (S > 1) {
+    const float ud = u[(long)(num_params(k, S) - 1) * ld];
+    const float sdr = sd * softplus(ud);
+    const float lg = logf(sdr);
+    const float z = (lg - sc[SC_DRIFT_MU * scld]) * (1.0f / 3.0f);
+    lp += -lg - 0.5f * z * z + log_sigmoid(ud);
+    const float q = sdr * (1.0f / S);
+    o.qd = q * q;
+  }
+  o.lp0 = lp;
+  return o;
+}
+
+// grad[i] = d/du_i [ log prior + log-det + log-lik ], given the filter adjoints
+// (Rb, qlb, qdb) and beta_bar = dloglik/dbeta (stride ld).
+CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int S,
+                                const float* __restrict__ sc, long scld,
+                                const float* __restrict__ beta_bar, float Rb, float qlb, float qdb,
+                                float* __restrict__ grad) {
+  const float sd = sc[SC_SD * scld];
+  {
+    const float u0 = u[0];
+    const float so = sd * softplus(u0);
+    const float dth = -(2.f * CI_PRIOR_A + 1.f) / so + 2.f * sc[SC_OBS_B * scld] / (so * so * so) + 2.f * so * Rb;
+    grad[0] = dth * sd * sigmoid(u0) + sigmoid(-u0);
+  }
+  {
+    const float u1 = u[ld];
+    const float sl = sd * softplus(u1);
+    const float dth = -(2.f * CI_PRIOR_A + 1.f) / sl + 2.f * sc[SC_LEVEL_B * scld] / (sl * sl * sl) + 2.f * sl * qlb;
+    grad[ld] = dth * sd * sigmoid(u1) + sigmoid(-u1);
+  }
+  if (k > 0) {
+    const float ug = u[2 * ld], un = u[3 * ld];
+    const float gsv = softplus(ug), gsn = softplus(un);
+    const float sq_gsv = sqrtf(gsv);
+    const float G = gsn * sq_gsv * CI_WEIGHTS_PRIOR_SCALE;
+    const float* ulsv = u + 4 * ld;
+    const float* ulsn = u + (long)(4 + k) * ld;
+    const float* uwn = u + (long)(4 + 2 * k) * ld;
+    float* glsv = grad + 4 * ld;
+    float* glsn = grad + (long)(4 + k) * ld;
+    float* gwn = grad + (long)(4 + 2 * k) * ld;
+    float dG = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float a = ulsv[(long)j * ld], b = ulsn[(long)j * ld], wn = uwn[(long)j * ld];
+      const float lsv = softplus(a), lsn = softplus(b);
+      const float sq = sqrtf(lsv);
+      const float l = lsn * sq;
+      const float bb = beta_bar[(long)j * ld];
+      dG = fmaf(bb, wn * l, dG);
+      gwn[(long)j * ld] = bb * l * G - wn;
+      const float dl = bb * wn * G;
+      glsn[(long)j * ld] = (dl * sq - lsn) * sigmoid(b) + sigmoid(-b);
+      glsv[(long)j * ld] = (dl * lsn * 0.5f / sq - 1.5f / lsv + 0.5f / (lsv * lsv)) * sigmoid(a) + sigmoid(-a);
+    }
+    grad[3 * ld] = (dG * sq_gsv * CI_WEIGHTS_PRIOR_SCALE - gsn) * sigmoid(un) + sigmoid(-un);
+    grad[2 * ld] = (dG * gsn * CI_WEIGHTS_PRIOR_SCALE * 0.5f / sq_gsv - 1.5f / gsv + 0.5f / (gsv * gsv)) * sigmoid(ug) +
+                   sigmoid(-ug);
+  }
+  if (S > 1) {
+    const long id = (long)(num_params(k, S) - 1) * ld;
+    const float ud = u[id];
+    const float sdr = sd * softplus(ud);
+    const float lg = logf(sdr);
+    const float dth = -1.0f / sdr - (lg - sc[SC_DRIFT_MU * scld]) / (9.0f * sdr) + 2.f * sdr * qdb * (1.0f / (S * S));
+    grad[id] = dth * sd * sigmoid(ud) + sigmoid(-ud);
+  }
+}
+
+// Constrained values theta[i] (same order/stride) from u -- what `model_samples` exposes.
+CI_HD void params_constrain_lane(const float* __restrict__ u, long ld, int k, int S, float sd,
+                                 float* __restrict__ theta, long ldo) {
+  theta[0] = sd * softplus(u[0]);
+  theta[ldo] = sd * softplus(u[ld]);
+  if (k > 0) {
+    for (int i = 2; i < 4 + 2 * k; ++i) theta[(long)i * ldo] = softplus(u[(long)i * ld]);
+    for (int i = 4 + 2 * k; i < 4 + 3 * k; ++i) theta[(long)i * ldo] = u[(long)i * ld];
+  }
+  if (S > 1) {
+    const long i = num_params(k, S) - 1;
+    theta[i * ldo] = sd * softplus(u[i * ld]);
+  }
+}
+
+}  // namespace ci
