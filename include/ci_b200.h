@@ -1,0 +1,166 @@
+/* ci_b200.h -- C ABI of the B200-native tfcausalimpact fit / forecast / reduction hot path.
+ *
+ * The reference (WillianFuks/tfcausalimpact v0.0.17) is pure Python and has NO native/FFI boundary
+ * of its own: its hot path is a dozen calls into the un-vendored tensorflow-probability package
+ * (causalimpact/model.py:216,235,291,306,311,319,361,370,374,414,446; inferences.py:108-145,397).
+ * Every entry point below therefore cites the reference *call site* whose work it replaces; the
+ * Python stub a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative CI_ERR_* otherwise, and never throws;
+ *    ci_last_error_string() describes the last failure on the calling thread.
+ *  - every `d_*` pointer is a caller-owned DEVICE pointer to contiguous float32 (unless noted);
+ *    nothing is allocated or freed inside (except the *_host convenience entry points, which own
+ *    their staging buffers), `stream` is a cudaStream_t passed as void*.  Calls are asynchronous
+ *    with respect to the host and re-entrant per stream.
+ *  - "lane" = one (series, chain[, sample]) evaluation; lanes are the FASTEST axis of every
+ *    per-lane array ([P][B] parameters, [T][B] residuals ...), lane b belongs to series b / G.
+ *  - arithmetic is float32, as the reference forces (causalimpact/data.py:274-275).
+ */
+#ifndef CI_B200_H_
+#define CI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CI_OK 0
+#define CI_ERR_INVALID_ARGUMENT (-1)
+#define CI_ERR_WORKSPACE_TOO_SMALL (-2)
+#define CI_ERR_UNSUPPORTED (-3)   /* layout outside the compiled set (e.g. nseasons not supported) */
+#define CI_ERR_CUDA (-4)          /* a CUDA runtime call failed; see ci_last_error_string() */
+
+#define CI_SCONST_FIELDS 8
+
+/* Fixed state-space layout of Sum([LocalLevel, SparseLinearRegression?, Seasonal?]) as built by
+ * causalimpact/model.py:239-321 (`build_default_model`). */
+typedef struct ci_layout {
+  int32_t N;    /* series in this call */
+  int32_t G;    /* lanes per series (chains x Monte-Carlo samples); B = N * G */
+  int32_t T;    /* observed (pre-period) steps */
+  int32_t Tf;   /* forecast (post-period) steps */
+  int32_t k;    /* covariates (0 = no regression component; model.py:298) */
+  int32_t S;    /* nseasons (1 = no seasonal component; model.py:310) */
+  int32_t r;    /* season_duration (model.py:313) */
+  int32_t Tpad; /* time stride of the packed design matrix: multiple of 4, >= T + Tf */
+} ci_layout;
+
+/* Caller-owned device inputs shared by every call on one batch of series. */
+typedef struct ci_data {
+  const float* d_y;      /* [N][T]        observed series, NaN = missing step            */
+  const float* d_X;      /* [N][k][Tpad]  packed design matrix (see ci_pack_design)      */
+  const float* d_sconst; /* [8][N]        per-series constants (see ci_series_stats)     */
+} ci_data;
+
+int ci_version(void);
+const char* ci_last_error_string(void);
+
+/* Number of scalar parameters of the layout: 2 + (k ? 2 + 3k : 0) + (S > 1).
+ * Order = tfp `model.parameters` (notebooks/getting_started.ipynb:2228-2236). */
+int ci_num_params(int32_t k, int32_t S);
+
+/* Empirical statistics + prior hyper-parameters per series.
+ * Replaces: tfp sts_util.empirical_statistics as used by LocalLevel/Seasonal/Sum, and
+ * causalimpact/model.py:283-290 (obs_sd, InverseGamma(16, 16 sigma^2) priors). */
+int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, float* d_sconst,
+                    void* stream);
+
+/* Row-major covariates [N][T+Tf][k] -> packed [N][k][Tpad] (time contiguous, NaN -> 0).
+ * Replaces: causalimpact/model.py:303-308 (concat(pre, post).astype(float32).fillna(0)). */
+int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, float* d_X_packed, void* stream);
+
+/* ---- K1-K3: joint log-prob + gradient in unconstrained space ------------------------------
+ * Replaces: `model.joint_log_prob(observed_time_series)` + TF autodiff, causalimpact/model.py:375-377
+ * (VI) and the target_log_prob_fn built inside tfp.sts.fit_with_hmc, model.py:361-364.
+ *   d_u    [P][B] in   unconstrained parameters
+ *   d_logp [B]    out  log p(y|theta) + log p(theta) + log|dtheta/du|
+ *   d_grad [P][B] out  gradient w.r.t. u                                                    */
+size_t ci_eval_workspace_bytes(const ci_layout* L);
+int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp,
+                        float* d_grad, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: mean-field ADVI ---------------------------------------------------------------------
+ * Replaces: tfp.sts.build_factored_surrogate_posterior + tfp.vi.fit_surrogate_posterior with
+ * Adam(0.1), causalimpact/model.py:367-381 (200 steps, 1 sample) and the 150 x 5 initialisation
+ * inside fit_with_hmc (model.py:361).  L->G must equal units_per_series * sample_size; lane
+ * b = unit * sample_size + sample, unit = series * units_per_series + chain.
+ *   d_mu, d_rho [P][U]  out  variational location / softplus^-1(scale), U = N * units_per_series
+ *   d_loss      [num_steps][U] out (may be NULL)  negative ELBO estimate per step             */
+size_t ci_vi_workspace_bytes(const ci_layout* L, int32_t units_per_series);
+int ci_vi_fit(const ci_layout* L, const ci_data* D, int32_t units_per_series, int32_t sample_size,
+              int32_t num_steps, float learning_rate, float init_scale, uint64_t seed, float* d_mu,
+              float* d_rho, float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* `surrogate_posterior.sample(num_draws)` (model.py:384) in unconstrained space:
+ *   d_u_out [P][U * num_draws], lane = unit * num_draws + draw.                              */
+int ci_vi_draw(int32_t P, int64_t U, int32_t num_draws, uint64_t seed, const float* d_mu,
+               const float* d_rho, float* d_u_out, void* stream);
+
+/* ---- K4: HMC with dual-averaging step-size adaptation ------------------------------------------
+ * Replaces: tfp.sts.fit_with_hmc -> mcmc.sample_chain(DualAveragingStepSizeAdaptation(
+ * TransformedTransitionKernel(HamiltonianMonteCarlo))), causalimpact/model.py:361-364.
+ * L->G = chains per series.  One lane = one chain.
+ *   d_u      [P][B]  in/out  current unconstrained state
+ *   d_step0  [P][B]  in      initial per-coordinate step sizes (VI stddevs, as fit_with_hmc)
+ *   d_draws  [num_results][P][B] out  unconstrained draws after warm-up
+ *   d_stats  [4][B] out  accept rate (sampling phase), accept rate (warm-up), final step factor,
+ *                        last log-prob                                                          */
+size_t ci_hmc_workspace_bytes(const ci_layout* L);
+int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_step0,
+               int32_t num_results, int32_t num_warmup, int32_t num_adapt, int32_t num_leapfrog,
+               float target_accept, uint64_t seed, int32_t iter_offset, float* d_draws,
+               float* d_stats, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Constrained parameter values theta [P][B] from u [P][B] (what `model_samples` exposes). */
+int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* d_theta, void* stream);
+
+/* ---- K6: filtering over the observed period per posterior draw ---------------------------------
+ * Replaces: tfp.sts.one_step_predictive (model.py:414-418) and the forward_filter half of
+ * tfp.sts.forecast (model.py:446-451).  L->G = posterior draws per series.
+ *   d_pred_mean, d_pred_var [T][B]  out  one-step-ahead predictive mean / variance of y_t
+ *   d_fstate [(S + S(S+1)/2 + S(S+1)/2)][B] out  predicted latent mean, packed covariance and its
+ *                                                packed lower Cholesky factor at step T         */
+size_t ci_predict_workspace_bytes(const ci_layout* L);
+int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, float* d_pred_mean,
+                      float* d_pred_var, float* d_fstate, void* d_workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- K7: posterior-predictive sampling ---------------------------------------------------------
+ * one_step_dist.sample(n) / .mean() and posterior_dist.sample(n) / .mean()
+ * (causalimpact/inferences.py:108,113,119,134; main.py:377), in ORIGINAL units
+ * (y * sigma + mu, misc.py:75-77; pass d_mu_sig = NULL when standardize=False).
+ *   d_mu_sig [2][N] (mu, sigma) or NULL
+ *   d_pre_sims  [N][nsamp][T]   d_pre_mean  [N][T]
+ *   d_post_sims [N][nsamp][Tf]  d_post_mean [N][Tf]                                            */
+int ci_onestep_sample(const ci_layout* L, const float* d_pred_mean, const float* d_pred_var,
+                      const float* d_mu_sig, int32_t nsamp, uint64_t seed, float* d_pre_sims,
+                      float* d_pre_mean, void* stream);
+int ci_forecast_sample(const ci_layout* L, const ci_data* D, const float* d_u, const float* d_fstate,
+                       const float* d_mu_sig, int32_t nsamp, uint64_t seed, float* d_post_sims,
+                       float* d_post_mean, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K8: sample reductions -----------------------------------------------------------------------
+ * Replaces: compile_posterior_inferences (inferences.py:119-206), summarize_posterior_inferences
+ * (inferences.py:311-352) and compute_p_value (inferences.py:397-408).
+ *   d_y_pre [N][T], d_y_post [N][Tf] observed series in original units (NaN in y_post = masked
+ *   step, dropped from every post-period statistic as `post_data[mask]` does)
+ *   d_inferences [N][16][T+Tf+1] out  the 16 columns of inferences.py:229-246; columns of the
+ *                                     pre+post kind use entries [0, T+Tf'), cumulative ones
+ *                                     [0, Tf'+1) (zero-prepended), Tf' = number of unmasked steps
+ *   d_summary    [N][21] out  10x2 summary table row-major (inferences.py:341-352) + p-value     */
+size_t ci_reduce_workspace_bytes(const ci_layout* L, int32_t nsamp);
+int ci_reduce_inferences(const ci_layout* L, const float* d_y_pre, const float* d_y_post,
+                         const float* d_pre_sims, const float* d_pre_mean, const float* d_post_sims,
+                         const float* d_post_mean, int32_t nsamp, float alpha, float* d_inferences,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+int ci_reduce_summary(const ci_layout* L, const float* d_y_post, const float* d_post_mean,
+                      const float* d_post_sims, int32_t nsamp, float alpha, float* d_summary,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CI_B200_H_ */

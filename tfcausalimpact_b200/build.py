@@ -1,0 +1,51 @@
+"""In-tree build of the sm_100a kernels + C-ABI into tfcausalimpact_b200/libci_b200.so.
+
+`nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo` on every csrc/*.cu (cross-compiles
+without a GPU).  The shared object is git-ignored but travels to the GPU box with the snapshot.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libci_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def _newest_source():
+    files = glob.glob(os.path.join(CSRC, '*.cu')) + glob.glob(os.path.join(CSRC, '*.cuh')) + \
+        glob.glob(os.path.join(HERE, '..', 'include', '*.h'))
+    return max(os.path.getmtime(f) for f in files)
+
+
+def needs_build():
+    return (not os.path.exists(LIB)) or os.path.getmtime(LIB) < _newest_source()
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    for src in sorted(glob.glob(os.path.join(CSRC, '*.cu'))):
+        obj = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.o')
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out.decode())
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}')
+    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'])
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

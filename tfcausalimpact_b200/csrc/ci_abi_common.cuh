@@ -1,0 +1,81 @@
+// Host-side plumbing shared by the C-ABI translation units: error string, argument checks,
+// workspace carving.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include "../../include/ci_b200.h"
+#include "ci_core.cuh"
+#include "ci_dispatch.cuh"
+#include "ci_params.cuh"
+
+namespace ci {
+
+char* last_error_buf();  // thread-local, defined in ci_eval.cu
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CI_CHECK_ARG(cond, msg) \
+  do { if (!(cond)) return ci::fail(CI_ERR_INVALID_ARGUMENT, "%s: %s", __func__, msg); } while (0)
+
+#define CI_CHECK_LAUNCH()                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = cudaPeekAtLastError();                                                 \
+    if (e_ != cudaSuccess) return ci::fail(CI_ERR_CUDA, "%s: %s", __func__, cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int check_layout(const ci_layout* L) {
+  if (!L) return fail(CI_ERR_INVALID_ARGUMENT, "layout is NULL");
+  if (L->N < 1 || L->G < 1 || L->T < 1 || L->Tf < 0 || L->k < 0 || L->S < 1 || L->r < 1)
+    return fail(CI_ERR_INVALID_ARGUMENT, "layout has a non-positive dimension");
+  if (L->S == 1 && L->r != 1) return fail(CI_ERR_INVALID_ARGUMENT, "season_duration > 1 needs nseasons > 1");
+  if (L->k > 0 && (L->Tpad % 4 != 0 || L->Tpad < L->T + L->Tf))
+    return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 4 and >= T + Tf");
+  return CI_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace (256-byte aligned slices).
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  float* floats(size_t n) {
+    float* r = reinterpret_cast<float*>(base + off);
+    off += align_up(n * sizeof(float), 256);
+    return r;
+  }
+};
+
+// Per-evaluation scratch (see ci_eval.cu).
+struct EvalWs {
+  float* beta;   // [max(k,1)][B]  beta, then beta_bar
+  float* scal;   // [8][B]  R, ql, qd, lp0, ll, Rb, qlb, qdb
+  float* resid;  // [T][B]  r_t, then dL/dr_t
+  float* tape;   // [T][S+2][B]
+};
+inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
+  const size_t B = (size_t)L->N * L->G;
+  const size_t nb = (size_t)(L->k > 0 ? L->k : 1) * B, ns = 8 * B, nr = (size_t)L->T * B,
+               nt = (size_t)L->T * (L->S + 2) * B;
+  if (ws && c) {
+    ws->beta = c->floats(nb);
+    ws->scal = c->floats(ns);
+    ws->resid = c->floats(nr);
+    ws->tape = c->floats(nt);
+  }
+  return align_up(nb * 4, 256) + align_up(ns * 4, 256) + align_up(nr * 4, 256) + align_up(nt * 4, 256);
+}
+
+// Enqueue one joint log-prob + gradient evaluation (5 kernels) on `stream`.
+int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                const EvalWs& ws, cudaStream_t stream);
+
+}  // namespace ci

@@ -66,7 +66,7 @@ template <int S>
 CI_HD void kf_predict(KState<S>& k, float ql, float qd, bool change) {
   k.P[tri<S>(0, 0)] += ql;
   if (S > 1 && change) {
-    constexpr int Z = S - 1;  // seasonal block size
+    constexpr int Z = (S > 1) ? S - 1 : 1;  // seasonal block size
     // mean: z'_i = z_{i+1}, z'_{Z-1} = -sum z
     float zs = 0.f;
 #pragma unroll
@@ -108,7 +108,7 @@ template <int S>
 CI_HD void kb_predict_adj(KState<S>& b, float& qlb, float& qdb, bool change) {
   qlb += b.P[tri<S>(0, 0)];
   if (S > 1 && change) {
-    constexpr int Z = S - 1;
+    constexpr int Z = (S > 1) ? S - 1 : 1;
     // qd touches every entry of the seasonal block
     float dsum = 0.f, osum = 0.f;
 #pragma unroll
