@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}')
-    subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'])
+    subprocess.check_call([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart'])
     return LIB
 
 

@@ -78,4 +78,11 @@ inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t stream);
 
+// out[t - t_lo][b] = with_y ? y_t - offset_t : offset_t, offset_t = mean + X_t . beta  (ci_eval.cu)
+void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, float* out, int t_lo, int t_hi,
+                    int with_y, cudaStream_t stream);
+// u -> beta [k][B], scal rows 0..3 = R, ql, qd, prior + log-det  (ci_eval.cu)
+void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
+                           cudaStream_t stream);
+
 }  // namespace ci

@@ -30,16 +30,18 @@ __global__ void k_params_forward(int N, int G, int k, int S, const float* __rest
   scal[3 * B + b] = ls.lp0;
 }
 
-// resid[t][b] = y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]; 4 time steps per 16-byte X load.
+// out[t - t_lo][b] for t in [t_lo, t_hi):  with_y ? y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]
+//                                                 : mean[n] + sum_j beta[j][b] X[n][j][t];
+// 4 time steps of one covariate per 16-byte X load.
 __global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ X,
                           const float* __restrict__ sconst, const float* __restrict__ beta,
-                          float* __restrict__ resid, int t_chunk) {
+                          float* __restrict__ out, int t_lo, int t_hi, int t_chunk, int with_y) {
   const long B = (long)L.N * L.G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / L.G);
-  const int tbeg = blockIdx.y * t_chunk;
-  const int tend = min(L.T, tbeg + t_chunk);
+  const int tbeg = (t_lo / 8) * 8 + blockIdx.y * t_chunk;
+  const int tend = min(t_hi, tbeg + t_chunk);
   const float mean = sconst[SC_MEAN * L.N + n];
   const float* __restrict__ Xn = X + (long)n * L.k * L.Tpad;
   const float* __restrict__ yn = y + (long)n * L.T;
@@ -60,9 +62,31 @@ __global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float*
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (t0 + i < tend) resid[(long)(t0 + i) * B + b] = __ldg(yn + t0 + i) + a[i];
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + i;
+      if (t >= t_lo && t < tend) out[(long)(t - t_lo) * B + b] = with_y ? __ldg(yn + t) + a[i] : -a[i];
+    }
   }
+}
+
+void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, float* out, int t_lo, int t_hi,
+                    int with_y, cudaStream_t st) {
+  const long B = (long)L->N * L->G;
+  const int bs = 128;
+  const unsigned gb = (unsigned)((B + bs - 1) / bs);
+  // enough (lane-block x time-chunk) CTAs to cover the machine a few times over
+  const int span = t_hi - (t_lo / 8) * 8;
+  int chunks = 1;
+  while ((long)gb * chunks < 148 * 8 && chunks * 8 < span) chunks *= 2;
+  const int t_chunk = ((span + chunks - 1) / chunks + 7) / 8 * 8;
+  chunks = (span + t_chunk - 1) / t_chunk;
+  k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo, t_hi, t_chunk, with_y);
+}
+
+void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
+                           cudaStream_t st) {
+  const long B = (long)L->N * L->G;
+  k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, beta, scal);
 }
 
 template <int S>
@@ -142,14 +166,7 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
   const int bs = 128;
   const unsigned gb = (unsigned)((B + bs - 1) / bs);
   k_params_forward<<<gb, bs, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, ws.beta, ws.scal);
-  {
-    // enough (lane-block x time-chunk) CTAs to cover the machine a few times over
-    int chunks = 1;
-    while ((long)gb * chunks < 148 * 8 && chunks * 8 < L->T) chunks *= 2;
-    int t_chunk = ((L->T + chunks - 1) / chunks + 7) / 8 * 8;
-    chunks = (L->T + t_chunk - 1) / t_chunk;
-    k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, ws.beta, ws.resid, t_chunk);
-  }
+  launch_offsets(L, D, ws.beta, ws.resid, 0, L->T, 1, st);
   CI_DISPATCH_S(L->S, (launch_kalman<S_>(L, D, ws, st)));
   if (L->k > 0) {
     constexpr int JT = 8;

@@ -90,3 +90,122 @@ class DeviceBatch:
                                                   ctypes.c_size_t(ws.numel()), nt.stream_ptr()),
                      'ci_kalman_logp_grad')
         return logp, grad
+
+    # ------------------------------------------------------------------------------------------
+    def _call(self, name, *args):
+        with torch.cuda.device(self.device):
+            nt.check(getattr(self.lib, name)(*args), name)
+
+    def _f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def vi_fit(self, units_per_series=1, sample_size=1, num_steps=200, learning_rate=0.1, init_scale=0.01,
+               seed=0, return_loss=False):
+        """Mean-field ADVI (model.py:367-381).  Returns mu[P,U], rho[P,U] (+ loss[num_steps,U])."""
+        U = self.N * units_per_series
+        L = self.layout(units_per_series * sample_size)
+        mu, rho = self._f32(self.P, U), self._f32(self.P, U)
+        loss = self._f32(num_steps, U) if return_loss else None
+        ws = self.workspace('fit', self.lib.ci_vi_workspace_bytes(ctypes.byref(L), ctypes.c_int32(units_per_series)))
+        D = self.data()
+        self._call('ci_vi_fit', ctypes.byref(L), ctypes.byref(D), ctypes.c_int32(units_per_series),
+                   ctypes.c_int32(sample_size), ctypes.c_int32(num_steps), ctypes.c_float(learning_rate),
+                   ctypes.c_float(init_scale), ctypes.c_uint64(seed), nt.ptr(mu), nt.ptr(rho), nt.ptr(loss),
+                   nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        return (mu, rho, loss) if return_loss else (mu, rho)
+
+    def vi_draw(self, mu, rho, num_draws, seed=0):
+        """`surrogate_posterior.sample(num_draws)` in unconstrained space: [P, U * num_draws]."""
+        U = mu.shape[1]
+        out = self._f32(self.P, U * num_draws)
+        self._call('ci_vi_draw', ctypes.c_int32(self.P), ctypes.c_int64(U), ctypes.c_int32(num_draws),
+                   ctypes.c_uint64(seed), nt.ptr(mu), nt.ptr(rho), nt.ptr(out), nt.stream_ptr())
+        return out
+
+    def hmc_run(self, u, step0, num_results=100, num_warmup=50, num_adapt=None, num_leapfrog=15,
+                target_accept=0.75, seed=0, iter_offset=0, draws=None):
+        """HMC + dual averaging (model.py:361-364).  u [P,B] is updated in place.
+        Returns draws [num_results, P, B] (unconstrained) and stats [4, B]."""
+        assert u.is_cuda and u.is_contiguous() and u.shape[0] == self.P
+        B = u.shape[1]
+        L = self.layout(B // self.N)
+        if num_adapt is None:
+            num_adapt = int(num_warmup * 0.8)
+        if draws is None:
+            draws = self._f32(max(num_results, 1), self.P, B)
+        stats = self._f32(4, B)
+        ws = self.workspace('fit', self.lib.ci_hmc_workspace_bytes(ctypes.byref(L)))
+        D = self.data()
+        self._call('ci_hmc_run', ctypes.byref(L), ctypes.byref(D), nt.ptr(u), nt.ptr(step0.contiguous()),
+                   ctypes.c_int32(num_results), ctypes.c_int32(num_warmup), ctypes.c_int32(num_adapt),
+                   ctypes.c_int32(num_leapfrog), ctypes.c_float(target_accept), ctypes.c_uint64(seed),
+                   ctypes.c_int32(iter_offset), nt.ptr(draws), nt.ptr(stats), nt.ptr(ws),
+                   ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        return draws[:num_results], stats
+
+    def constrain(self, u):
+        """Constrained parameter values theta [P,B] (what `model_samples` exposes)."""
+        B = u.shape[1]
+        L = self.layout(B // self.N)
+        theta = torch.empty_like(u)
+        D = self.data()
+        self._call('ci_constrain', ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()), nt.ptr(theta),
+                   nt.stream_ptr())
+        return theta
+
+    # ---- predictive path ---------------------------------------------------------------------
+    def filter_predict(self, u):
+        """One-step-ahead predictive mean/variance [T,B] per draw + forecast prior state."""
+        B = u.shape[1]
+        L = self.layout(B // self.N)
+        S = self.S
+        nfs = S + S * (S + 1)
+        pm, pv, fs = self._f32(self.T, B), self._f32(self.T, B), self._f32(nfs, B)
+        ws = self.workspace('pred', self.lib.ci_predict_workspace_bytes(ctypes.byref(L)))
+        D = self.data()
+        self._call('ci_filter_predict', ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()), nt.ptr(pm),
+                   nt.ptr(pv), nt.ptr(fs), nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        return pm, pv, fs
+
+    def onestep_sample(self, pm, pv, nsamp, seed=0, mu_sig=None, want_mean=True):
+        B = pm.shape[1]
+        L = self.layout(B // self.N)
+        sims = self._f32(self.N, nsamp, self.T) if nsamp > 0 else None
+        mean = self._f32(self.N, self.T) if want_mean else None
+        self._call('ci_onestep_sample', ctypes.byref(L), nt.ptr(pm), nt.ptr(pv), nt.ptr(mu_sig),
+                   ctypes.c_int32(nsamp), ctypes.c_uint64(seed), nt.ptr(sims), nt.ptr(mean), nt.stream_ptr())
+        return sims, mean
+
+    def forecast_sample(self, u, fs, nsamp, seed=0, mu_sig=None, want_mean=True):
+        B = u.shape[1]
+        L = self.layout(B // self.N)
+        sims = self._f32(self.N, nsamp, self.Tf) if nsamp > 0 else None
+        mean = self._f32(self.N, self.Tf) if want_mean else None
+        ws = self.workspace('pred', self.lib.ci_predict_workspace_bytes(ctypes.byref(L)))
+        D = self.data()
+        self._call('ci_forecast_sample', ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()), nt.ptr(fs),
+                   nt.ptr(mu_sig), ctypes.c_int32(nsamp), ctypes.c_uint64(seed), nt.ptr(sims), nt.ptr(mean),
+                   nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        return sims, mean
+
+    # ---- reductions --------------------------------------------------------------------------
+    def reduce_inferences(self, y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):
+        """16 inference columns [N,16,T+Tf+1] (inferences.py:229-246); inputs in original units."""
+        nsamp = pre_sims.shape[1]
+        L = self.layout(1)
+        out = self._f32(self.N, 16, self.T + self.Tf + 1)
+        ws = self.workspace('red', self.lib.ci_reduce_workspace_bytes(ctypes.byref(L), ctypes.c_int32(nsamp)))
+        self._call('ci_reduce_inferences', ctypes.byref(L), nt.ptr(y_pre), nt.ptr(y_post), nt.ptr(pre_sims),
+                   nt.ptr(pre_mean), nt.ptr(post_sims), nt.ptr(post_mean), ctypes.c_int32(nsamp),
+                   ctypes.c_float(alpha), nt.ptr(out), nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        return out
+
+    def reduce_summary(self, y_post, post_mean, post_sims, alpha):
+        """[N,21]: the 10x2 summary table row-major (inferences.py:341-352) + p-value (:397-408)."""
+        nsamp = post_sims.shape[1]
+        L = self.layout(1)
+        out = self._f32(self.N, 21)
+        self._call('ci_reduce_summary', ctypes.byref(L), nt.ptr(y_post), nt.ptr(post_mean), nt.ptr(post_sims),
+                   ctypes.c_int32(nsamp), ctypes.c_float(alpha), nt.ptr(out), ctypes.c_void_p(0),
+                   ctypes.c_size_t(0), nt.stream_ptr())
+        return out
