@@ -1,0 +1,139 @@
+"""End-to-end `CausalImpact(...)` on the GPU against the reference's published / tested answers
+(README.md:61-72 arma table, README.md:138-149 comparison table, tests/test_main.py:299-340).
+RNG parity with TensorFlow is impossible, so agreement is statistical: posterior-mean prediction
+within a fraction of the published s.d., interval half-widths within a tolerance band."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _ci(*a, **k):
+    from tfcausalimpact_b200 import CausalImpact
+    return CausalImpact(*a, **k)
+
+
+def test_arma_readme_table_vi():
+    data = pd.read_csv(os.path.join(GOLD, 'arma_data.csv'))[['y', 'X']]
+    data.iloc[70:, 0] += 5
+    np.random.seed(123)
+    ci = _ci(data, [0, 69], [70, 99])
+    s = ci.summary_data
+    assert abs(s.loc['actual', 'average'] - 125.23) < 0.01
+    assert abs(s.loc['actual', 'cumulative'] - 3756.86) < 0.05
+    # README: prediction 120.34 (0.31) [119.76, 120.97]
+    assert abs(s.loc['predicted', 'average'] - 120.34) < 0.25
+    half = (s.loc['predicted_upper', 'average'] - s.loc['predicted_lower', 'average']) / 2
+    assert 0.3 < half < 1.2
+    assert abs(s.loc['abs_effect', 'average'] - 4.89) < 0.25
+    assert abs(s.loc['rel_effect', 'average'] - 0.0406) < 0.003
+    assert ci.p_value < 0.01
+    assert ci.model_kernel_results is None
+    assert isinstance(ci.model_samples, dict) and len(ci.model_samples) == 7
+    assert tuple(ci.model_samples['SparseLinearRegression/_weights_noncentered'].shape) == (100, 1)
+    assert list(ci.inferences.columns)[0] == 'complete_preds_means' and ci.inferences.shape == (100, 16)
+    assert isinstance(ci.inferences.index, pd.RangeIndex)
+    out = ci.summary()
+    assert out.startswith('Posterior Inference {Causal Impact}') and '95% CI' in out
+    assert 'p = ' in ci.summary('report')
+
+
+def test_arma_known_answer_integer_parts():
+    """tests/test_main.py:299-313 of the reference: column 0 (= X) is the response."""
+    data = pd.read_csv(os.path.join(GOLD, 'arma_data.csv'))
+    data.iloc[70:, 0] += 5
+    np.random.seed(123)
+    ci = _ci(data, [0, 69], [70, 99])
+    avg = ci.summary_data['average']
+    assert int(avg['actual']) == 105
+    assert int(avg['predicted']) == 100
+    assert int(avg['predicted_lower']) == 99
+    assert int(avg['predicted_upper']) == 100
+    assert int(avg['abs_effect']) == 5
+    assert int(avg['abs_effect_lower']) == 4
+    assert int(avg['abs_effect_upper']) == 5
+
+
+def test_comparison_readme_table_hmc():
+    data = pd.read_csv(os.path.join(GOLD, 'comparison_data.csv'), index_col=['DATE'])
+    np.random.seed(7)
+    ci = _ci(data, ['2019-04-16', '2019-07-14'], ['2019-7-15', '2019-08-01'], model_args={'fit_method': 'hmc'})
+    s = ci.summary_data
+    assert abs(s.loc['actual', 'average'] - 78574.42) < 0.5
+    assert abs(s.loc['actual', 'cumulative'] - 1414339.5) < 5
+    # README: 79282.92 (727.48) [77849.5, 80701.18]; R package: 79232 (736)
+    assert abs(s.loc['predicted', 'average'] - 79282.92) < 400
+    sd = (s.loc['predicted_upper', 'average'] - s.loc['predicted_lower', 'average']) / (2 * 1.96)
+    assert 500 < sd < 1000
+    assert 0.03 < ci.p_value < 0.45
+    assert isinstance(ci.model_samples, list) and len(ci.model_samples) == 7
+    assert tuple(ci.model_samples[6].shape) == (100, 3)
+    kr = ci.model_kernel_results
+    assert 0.3 < kr['accept_rate'] <= 1.0
+    assert isinstance(ci.inferences.index, pd.DatetimeIndex)
+
+
+def test_sparse_regression_shrinks_irrelevant_weight():
+    """tests/test_main.py:316-340 of the reference: abs(mean weight of X2) < 0.05."""
+    data = pd.read_csv(os.path.join(GOLD, 'arma_sparse_reg.csv'))
+    data.iloc[70:, 0] += 5
+    np.random.seed(123)
+    ci = _ci(data, [0, 69], [70, 99])
+    ms = ci.model_samples
+    gs = (ms['SparseLinearRegression/_global_scale_noncentered'] *
+          ms['SparseLinearRegression/_global_scale_variance'].sqrt() * 0.1)
+    ls = (ms['SparseLinearRegression/_local_scales_noncentered'] *
+          ms['SparseLinearRegression/_local_scale_variances'].sqrt())
+    w = (ms['SparseLinearRegression/_weights_noncentered'] * ls * gs[:, None]).mean(dim=0)
+    assert abs(float(w[1])) < 0.05
+    assert float(w[0]) > 0.3
+
+
+def test_seasons_no_standardize_and_gaps():
+    """Missing calendar days become NaN rows after regularisation: pre-period NaNs are skipped by
+    the filter, post-period ones are masked out of every statistic (reference issue #51,
+    tests/test_main.py:360-380)."""
+    rng = np.random.default_rng(0)
+    n = 140
+    idx = pd.date_range('2021-01-04', periods=n)
+    x = rng.normal(size=n).cumsum() * 0.1 + 10
+    y = 2.0 * x + rng.normal(scale=0.2, size=n) + np.tile([0.5, -0.2, 0.1, -0.4, 0.0, 0.3, -0.3], n // 7)
+    y[100:] += 1.0
+    df = pd.DataFrame({'y': y, 'x': x}, index=idx)
+    drop = [idx[40], idx[41], idx[103], idx[104], idx[130]]
+    df = df[~df.index.isin(drop)]
+    np.random.seed(1)
+    ci = _ci(df, [idx[0], idx[99]], [idx[100], idx[-1]],
+             model_args={'nseasons': 7, 'standardize': False, 'niter': 500})
+    assert ci.model.components[2].num_seasons == 7
+    assert ci.mu_sig is None and ci.normed_pre_data is None
+    expected_mask = np.ones(40, dtype=bool)
+    expected_mask[[3, 4, 30]] = False
+    np.testing.assert_array_equal(ci._mask, expected_mask)
+    assert len(ci.pre_data) == 100 and int(ci.pre_data.iloc[:, 0].isna().sum()) == 2
+    assert len(ci.inferences) == 100 + 37
+    assert idx[103] not in ci.inferences.index
+    assert np.isfinite(ci.inferences['complete_preds_means'].values).all()
+    assert 0.4 < ci.summary_data.loc['abs_effect', 'average'] < 1.6
+    assert 0 <= ci.p_value < 0.2
+
+
+def test_custom_model_and_rejection():
+    from tfcausalimpact_b200 import model as M
+    data = pd.read_csv(os.path.join(GOLD, 'arma_data.csv'))[['y', 'X']].astype(np.float32)
+    data.iloc[70:, 0] += 5
+    pre = data.iloc[:70]
+    normed = (data - pre.mean()) / pre.std(ddof=0)
+    obs = pd.DataFrame(normed.iloc[:70, 0])
+    model = M.Sum([M.LocalLevel(M.build_bijector(M.build_inv_gamma_sd_prior(0.05))),
+                   M.SparseLinearRegression(normed.iloc[:, 1:])], observed_time_series=obs)
+    np.random.seed(5)
+    ci = _ci(data, [0, 69], [70, 99], model=model)
+    assert abs(ci.summary_data.loc['abs_effect', 'average'] - 4.9) < 0.5
+    with pytest.raises(ValueError):
+        _ci(data, [0, 69], [70, 99], model=object())

@@ -22,7 +22,7 @@ class DeviceBatch:
         nt.require_cuda()
         self.lib = nt.lib()
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
-        y = torch.as_tensor(np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y)
+        y = torch.as_tensor(np.array(y, dtype=np.float32) if not torch.is_tensor(y) else y)
         if y.dim() == 1:
             y = y[None, :]
         self.y = y.to(self.device, torch.float32).contiguous()
@@ -31,7 +31,7 @@ class DeviceBatch:
         if X is None:
             self.k = 0
         else:
-            X = torch.as_tensor(np.asarray(X, dtype=np.float32) if not torch.is_tensor(X) else X)
+            X = torch.as_tensor(np.array(X, dtype=np.float32) if not torch.is_tensor(X) else X)
             if X.dim() == 2:
                 X = X[None]
             assert X.shape[0] == self.N and X.shape[1] == self.T + self.Tf, \
@@ -190,22 +190,74 @@ class DeviceBatch:
 
     # ---- reductions --------------------------------------------------------------------------
     def reduce_inferences(self, y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):
-        """16 inference columns [N,16,T+Tf+1] (inferences.py:229-246); inputs in original units."""
-        nsamp = pre_sims.shape[1]
-        L = self.layout(1)
-        out = self._f32(self.N, 16, self.T + self.Tf + 1)
-        ws = self.workspace('red', self.lib.ci_reduce_workspace_bytes(ctypes.byref(L), ctypes.c_int32(nsamp)))
-        self._call('ci_reduce_inferences', ctypes.byref(L), nt.ptr(y_pre), nt.ptr(y_post), nt.ptr(pre_sims),
-                   nt.ptr(pre_mean), nt.ptr(post_sims), nt.ptr(post_mean), ctypes.c_int32(nsamp),
-                   ctypes.c_float(alpha), nt.ptr(out), nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
-        return out
+        return reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha)
 
     def reduce_summary(self, y_post, post_mean, post_sims, alpha):
-        """[N,21]: the 10x2 summary table row-major (inferences.py:341-352) + p-value (:397-408)."""
-        nsamp = post_sims.shape[1]
-        L = self.layout(1)
-        out = self._f32(self.N, 21)
-        self._call('ci_reduce_summary', ctypes.byref(L), nt.ptr(y_post), nt.ptr(post_mean), nt.ptr(post_sims),
-                   ctypes.c_int32(nsamp), ctypes.c_float(alpha), nt.ptr(out), ctypes.c_void_p(0),
-                   ctypes.c_size_t(0), nt.stream_ptr())
-        return out
+        return reduce_summary(y_post, post_mean, post_sims, alpha)
+
+    # ---- host-side conveniences (plumbing, not on the hot path) ---------------------------------
+    def set_obs_prior_scale(self, scale):
+        """Override the InverseGamma scale of the observation-noise variance prior (the device
+        default is 16 (sd_y / 2)^2, model.py:289-290) and patch the prior constant accordingly."""
+        new = torch.full((self.N,), float(scale), dtype=torch.float32, device=self.device)
+        old = self.sconst[4].clone()
+        if torch.allclose(old, new, rtol=1e-5, atol=0.0):
+            return
+        self.sconst[7] += 16.0 * (torch.log(new) - torch.log(old))
+        self.sconst[4] = new
+
+    def unconstrain(self, theta):
+        """Inverse of `constrain`: theta [P,B] -> u [P,B] (torch ops; used once per fit)."""
+        B = theta.shape[1]
+        G = B // self.N
+        sd = self.sconst[1].repeat_interleave(G)[None, :]
+
+        def sp_inv(x):
+            return x + torch.log(-torch.expm1(-x))
+        u = theta.clone()
+        k = self.k
+        u[0:2] = sp_inv(theta[0:2] / sd)
+        if k > 0:
+            u[2:4 + 2 * k] = sp_inv(theta[2:4 + 2 * k])
+        if self.S > 1:
+            u[self.P - 1] = sp_inv(theta[self.P - 1] / sd[0])
+        return u.contiguous()
+
+
+def _layout_for(N, T, Tf):
+    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 3) // 4 * 4)
+
+
+def reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):
+    """Device reduction of compile_posterior_inferences (inferences.py:119-206).
+    y_pre [N,T], y_post [N,Tf] (NaN = masked), pre_sims [N,n,T], post_sims [N,n,Tf] -> [N,16,T+Tf+1]."""
+    nt.require_cuda()
+    lib = nt.lib()
+    N, T = y_pre.shape
+    Tf, nsamp = y_post.shape[1], pre_sims.shape[1]
+    L = _layout_for(N, T, Tf)
+    dev = y_pre.device
+    out = torch.empty((N, 16, T + Tf + 1), dtype=torch.float32, device=dev)
+    nbytes = lib.ci_reduce_workspace_bytes(ctypes.byref(L), ctypes.c_int32(nsamp))
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        nt.check(lib.ci_reduce_inferences(ctypes.byref(L), nt.ptr(y_pre), nt.ptr(y_post), nt.ptr(pre_sims),
+                                          nt.ptr(pre_mean), nt.ptr(post_sims), nt.ptr(post_mean),
+                                          ctypes.c_int32(nsamp), ctypes.c_float(alpha), nt.ptr(out), nt.ptr(ws),
+                                          ctypes.c_size_t(ws.numel()), nt.stream_ptr()), 'ci_reduce_inferences')
+    return out
+
+
+def reduce_summary(y_post, post_mean, post_sims, alpha):
+    """Device reduction of summarize_posterior_inferences + compute_p_value -> [N,21]."""
+    nt.require_cuda()
+    lib = nt.lib()
+    N, Tf = y_post.shape
+    nsamp = post_sims.shape[1]
+    L = _layout_for(N, 1, Tf)
+    out = torch.empty((N, 21), dtype=torch.float32, device=y_post.device)
+    with torch.cuda.device(y_post.device):
+        nt.check(lib.ci_reduce_summary(ctypes.byref(L), nt.ptr(y_post), nt.ptr(post_mean), nt.ptr(post_sims),
+                                       ctypes.c_int32(nsamp), ctypes.c_float(alpha), nt.ptr(out),
+                                       ctypes.c_void_p(0), ctypes.c_size_t(0), nt.stream_ptr()), 'ci_reduce_summary')
+    return out
