@@ -160,6 +160,11 @@ int ci_reduce_summary(const ci_layout* L, const float* d_y_post, const float* d_
                       const float* d_post_sims, int32_t nsamp, float alpha, float* d_summary,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* FP32-FMA throughput probe used by bench.py as the measured CUDA-core roofline denominator
+ * (MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only): `blocks` CTAs of 256 threads, 16
+ * independent FMA chains per thread, `iters` rounds; *flops_out = FLOPs the launch performs. */
+int ci_bench_fma(int32_t iters, int32_t blocks, float* d_out, void* stream, double* flops_out);
+
 #ifdef __cplusplus
 }
 #endif

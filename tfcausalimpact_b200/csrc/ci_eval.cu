@@ -310,3 +310,29 @@ int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* 
 }
 
 }  // extern "C"
+
+// ---- FP32-FMA peak probe (roofline denominator for the CUDA-core-bound kernels) -----------------
+namespace ci {
+__global__ void __launch_bounds__(256) k_fma_probe(int iters, float seed, float* __restrict__ out) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 0.999f + seed * 1e-6f, c = 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+}  // namespace ci
+
+extern "C" int ci_bench_fma(int32_t iters, int32_t blocks, float* d_out, void* stream, double* flops_out) {
+  CI_CHECK_ARG(iters > 0 && blocks > 0 && d_out, "bad arguments");
+  ci::k_fma_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, d_out);
+  if (flops_out) *flops_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+  CI_CHECK_LAUNCH();
+  return CI_OK;
+}
