@@ -49,14 +49,14 @@ def synth_problem(N, T, Tf, k, S, r=1, seed=0, nan_frac=0.0, standardize=True):
 
 
 def pack_X(X, Tpad=None):
-    """[N, Ttot, k] -> [N, k, Tpad] time-contiguous, zero padded to a multiple of 4."""
+    """[N, Ttot, k] -> chunk-major [N, Tpad/8, k, 8], zero padded to a multiple of 8 steps."""
     N, Tt, k = X.shape
     if Tpad is None:
-        Tpad = (Tt + 3) // 4 * 4
-    out = np.zeros((N, max(k, 1), Tpad), dtype=np.float32)
-    if k > 0:
-        out[:, :k, :Tt] = np.transpose(X, (0, 2, 1))
-    return out[:, :k, :] if k > 0 else out[:, :0, :], Tpad
+        Tpad = (Tt + 7) // 8 * 8
+    buf = np.zeros((N, Tpad, k), dtype=np.float32)
+    buf[:, :Tt, :] = X
+    out = np.ascontiguousarray(buf.reshape(N, Tpad // 8, 8, k).transpose(0, 1, 3, 2))
+    return out, Tpad
 
 
 def prior_const(L: 'O.Layout', obs_b, level_b, sd):

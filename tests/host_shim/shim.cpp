@@ -5,43 +5,26 @@
 #include <cstring>
 #include <vector>
 #include "ci_core.cuh"
-#include "ci_kalman.cuh"
-#include "ci_params.cuh"
+#include "ci_eval_lane.cuh"
 #include "ci_dispatch.cuh"
 
 using namespace ci;
 
 template <int S>
-static void lane_eval(float* resid, float* tape, long ld, int T, int r, LaneScalars ls, float m0, float p0,
-                      float& ll, float& Rb, float& qlb, float& qdb) {
-  kalman_logp_grad_lane<S>(resid, tape, ld, T, r, ls.R, ls.ql, ls.qd, m0, p0, ll, Rb, qlb, qdb);
+static void lane_eval(const float* u, long B, const float* sc, int N, const float* yn, const float* Xn, int T, int k,
+                      int r, float* sb, float* sr, float* tape, float* logp, float* grad) {
+  eval_lane<S>(u, B, sc, N, yn, Xn, T, k, r, sb, 1, sr, 4, tape, 1, logp, grad);
 }
 
+// Runs ci::eval_lane -- the exact per-lane function the CUDA kernel k_eval executes -- for every lane.
 extern "C" int shim_logp_grad(int N, int G, int T, int k, int S, int r, const float* y, const float* X,
                               int Tpad, const float* sconst, const float* u, float* logp, float* grad) {
   const long B = (long)N * G;
-  const int P = num_params(k, S);
-  (void)P;
-  std::vector<float> beta((size_t)(k > 0 ? k : 1) * B), resid((size_t)T * B), tape((size_t)T * (S + 2) * B);
+  std::vector<float> sb((size_t)(k > 0 ? k : 1)), sr(8), tape((size_t)T * (S + 2));
   for (long b = 0; b < B; ++b) {
     const int n = (int)(b / G);
-    const float* sc = sconst + n;
-    LaneScalars ls = params_forward_lane(u + b, B, k, S, sc, N, beta.data() + b);
-    for (int t = 0; t < T; ++t) {
-      float acc = y[(long)n * T + t] - sc[SC_MEAN * N];
-      for (int j = 0; j < k; ++j) acc -= beta[(size_t)j * B + b] * X[((long)n * k + j) * Tpad + t];
-      resid[(size_t)t * B + b] = acc;
-    }
-    float ll = 0, Rb = 0, qlb = 0, qdb = 0;
-    const float m0 = sc[SC_M0 * N], p0 = sc[SC_P0 * N];
-    CI_DISPATCH_S(S, (lane_eval<S_>(resid.data() + b, tape.data() + b, B, T, r, ls, m0, p0, ll, Rb, qlb, qdb)));
-    for (int j = 0; j < k; ++j) {
-      float acc = 0.f;
-      for (int t = 0; t < T; ++t) acc -= resid[(size_t)t * B + b] * X[((long)n * k + j) * Tpad + t];
-      beta[(size_t)j * B + b] = acc;
-    }
-    params_backward_lane(u + b, B, k, S, sc, N, beta.data() + b, Rb, qlb, qdb, grad + b);
-    logp[b] = ll + ls.lp0;
+    CI_DISPATCH_S(S, (lane_eval<S_>(u + b, B, sconst + n, N, y + (long)n * T, X + (long)n * k * Tpad, T, k, r,
+                                    sb.data(), sr.data(), tape.data(), logp + b, grad + b)));
   }
   return 0;
 }

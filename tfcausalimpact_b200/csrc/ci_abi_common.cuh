@@ -35,8 +35,8 @@ inline int check_layout(const ci_layout* L) {
   if (L->N < 1 || L->G < 1 || L->T < 1 || L->Tf < 0 || L->k < 0 || L->S < 1 || L->r < 1)
     return fail(CI_ERR_INVALID_ARGUMENT, "layout has a non-positive dimension");
   if (L->S == 1 && L->r != 1) return fail(CI_ERR_INVALID_ARGUMENT, "season_duration > 1 needs nseasons > 1");
-  if (L->k > 0 && (L->Tpad % 4 != 0 || L->Tpad < L->T + L->Tf))
-    return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 4 and >= T + Tf");
+  if (L->k > 0 && (L->Tpad % 8 != 0 || L->Tpad < L->T + L->Tf))
+    return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 8 and >= T + Tf");
   return CI_OK;
 }
 
@@ -54,27 +54,18 @@ struct Carver {
   }
 };
 
-// Per-evaluation scratch (see ci_eval.cu).
+// Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
-  float* beta;   // [max(k,1)][B]  beta, then beta_bar
-  float* scal;   // [8][B]  R, ql, qd, lp0, ll, Rb, qlb, qdb
-  float* resid;  // [T][B]  r_t, then dL/dr_t
   float* tape;   // [T][S+2][B]
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   const size_t B = (size_t)L->N * L->G;
-  const size_t nb = (size_t)(L->k > 0 ? L->k : 1) * B, ns = 8 * B, nr = (size_t)L->T * B,
-               nt = (size_t)L->T * (L->S + 2) * B;
-  if (ws && c) {
-    ws->beta = c->floats(nb);
-    ws->scal = c->floats(ns);
-    ws->resid = c->floats(nr);
-    ws->tape = c->floats(nt);
-  }
-  return align_up(nb * 4, 256) + align_up(ns * 4, 256) + align_up(nr * 4, 256) + align_up(nt * 4, 256);
+  const size_t nt = (size_t)L->T * (L->S + 2) * B;
+  if (ws && c) ws->tape = c->floats(nt);
+  return align_up(nt * 4, 256);
 }
 
-// Enqueue one joint log-prob + gradient evaluation (5 kernels) on `stream`.
+// Enqueue one joint log-prob + gradient evaluation (one kernel) on `stream`.
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t stream);
 

@@ -1,19 +1,43 @@
-// K1-K3: joint log-prob + gradient of the fixed-layout structural time-series model.
-//   k_params_forward : u -> (R, ql, qd, prior+logdet), beta                     [thread per lane]
-//   k_offsets        : r_t = y_t - mean - X_t . beta                            [lane x time tile]
-//   k_kalman<S>      : Kalman log-lik + reverse-time adjoint, registers only    [thread per lane]
-//   k_beta_bar       : dL/dbeta_j = -sum_t rbar_t X_tj                          [lane x covariate tile]
-//   k_params_backward: VJP through horseshoe / softplus / sqrt + prior gradient [thread per lane]
-// Lanes are the fastest axis of every array, so each warp access is one 128 B line; the packed
-// design matrix is time-contiguous so a thread pulls 4 steps of one covariate per 16 B load.
+// K1-K3: joint log-prob + gradient of the fixed-layout structural time-series model, ONE kernel:
+//   k_eval<S>  -- thread per (series, chain[, sample]) lane; per lane (ci_eval_lane.cuh):
+//        u -> sigma^2's, beta (shared-memory column)                                [K3 forward]
+//        per 8-step chunk: r = y - mean - X beta (two 16-byte loads per covariate), 8 Kalman steps,
+//        tape (g, s, v) -> HBM                                                       [K2 + K1 forward]
+//        reverse sweep with software-pipelined tape reads, beta_bar += rbar X per chunk
+//        VJP through horseshoe / softplus / sqrt + priors -> grad                   [K1-K3 reverse]
+// Lanes are the fastest axis of every per-lane array ([P][B] parameters, [T][S+2][B] tape), so each
+// warp access is one 128 B line; the design matrix is chunk-major [N][Tpad/8][k][8] so the lanes of a
+// CTA stream contiguous 32k-byte runs.  Mean, packed covariance and their adjoints stay in
+// registers for the whole evaluation; nothing but the tape is spilled to HBM.
+//   k_params_forward / k_offsets -- u -> beta / offsets for the predictive path (ci_predict.cu).
 #include "ci_abi_common.cuh"
-#include "ci_kalman.cuh"
+#include "ci_eval_lane.cuh"
 
 namespace ci {
 
 char* last_error_buf() {
   static thread_local char buf[512] = "";
   return buf;
+}
+
+constexpr int EVAL_THREADS = 64;
+
+// Registers are capped so that >= 640 lanes stay resident per SM for the small latent sizes
+// (S <= 7 -> <= 102 registers): 148 SMs x 640 = 94,720 lanes, i.e. the 80,000 lanes of the headline
+// workload run as ONE wave (the run time of a lane is fixed by its T sequential steps).
+template <int S>
+__global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
+k_eval(ci_layout L, const float* __restrict__ y, const float* __restrict__ X, const float* __restrict__ sconst,
+       const float* __restrict__ u, float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
+  extern __shared__ __align__(16) float smem[];
+  const long B = (long)L.N * L.G;
+  const long b = (long)blockIdx.x * EVAL_THREADS + threadIdx.x;
+  if (b >= B) return;
+  const int n = (int)(b / L.G);
+  float* sr = smem + threadIdx.x * 4;                     // [2][EVAL_THREADS][4]
+  float* sb = smem + 8 * EVAL_THREADS + threadIdx.x;      // [k][EVAL_THREADS]
+  eval_lane<S>(u + b, B, sconst + n, L.N, y + (long)n * L.T, X + (long)n * L.k * L.Tpad, L.T, L.k, L.r, sb,
+               EVAL_THREADS, sr, 4 * EVAL_THREADS, tape + b, B, logp + b, grad + b);
 }
 
 __global__ void k_params_forward(int N, int G, int k, int S, const float* __restrict__ sconst,
@@ -23,7 +47,7 @@ __global__ void k_params_forward(int N, int G, int k, int S, const float* __rest
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / G);
-  LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, N, beta + b);
+  LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, N, beta + b, B);
   scal[0 * B + b] = ls.R;
   scal[1 * B + b] = ls.ql;
   scal[2 * B + b] = ls.qd;
@@ -32,40 +56,34 @@ __global__ void k_params_forward(int N, int G, int k, int S, const float* __rest
 
 // out[t - t_lo][b] for t in [t_lo, t_hi):  with_y ? y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]
 //                                                 : mean[n] + sum_j beta[j][b] X[n][j][t];
-// 4 time steps of one covariate per 16-byte X load.
+// one (lane, 8-step chunk) per thread.  Used by the predictive path only.
 __global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ X,
                           const float* __restrict__ sconst, const float* __restrict__ beta,
-                          float* __restrict__ out, int t_lo, int t_hi, int t_chunk, int with_y) {
+                          float* __restrict__ out, int t_lo, int t_hi, int with_y) {
   const long B = (long)L.N * L.G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / L.G);
-  const int tbeg = (t_lo / 8) * 8 + blockIdx.y * t_chunk;
-  const int tend = min(t_hi, tbeg + t_chunk);
+  const int tc = t_lo / 8 + blockIdx.y;
+  const int t0 = tc * 8;
+  if (t0 >= t_hi) return;
   const float mean = sconst[SC_MEAN * L.N + n];
-  const float* __restrict__ Xn = X + (long)n * L.k * L.Tpad;
-  const float* __restrict__ yn = y + (long)n * L.T;
-  for (int t0 = tbeg; t0 < tend; t0 += 8) {
-    float a[8];
+  float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = -mean;
-    const bool second = (t0 + 4 < L.Tpad);
-    for (int j = 0; j < L.k; ++j) {
-      const float bj = beta[(long)j * B + b];
-      const float4 x0 = __ldg(reinterpret_cast<const float4*>(Xn + (long)j * L.Tpad + t0));
-      a[0] = fmaf(-bj, x0.x, a[0]); a[1] = fmaf(-bj, x0.y, a[1]);
-      a[2] = fmaf(-bj, x0.z, a[2]); a[3] = fmaf(-bj, x0.w, a[3]);
-      if (second) {
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(Xn + (long)j * L.Tpad + t0 + 4));
-        a[4] = fmaf(-bj, x1.x, a[4]); a[5] = fmaf(-bj, x1.y, a[5]);
-        a[6] = fmaf(-bj, x1.z, a[6]); a[7] = fmaf(-bj, x1.w, a[7]);
-      }
-    }
+  for (int i = 0; i < 8; ++i) a[i] = -mean;
+  const float* __restrict__ xp = X + ((long)n * (L.Tpad / 8) + tc) * L.k * 8;
+  for (int j = 0; j < L.k; ++j) {
+    const float bj = beta[(long)j * B + b];
+    const f4 x0 = load4(xp + j * 8), x1 = load4(xp + j * 8 + 4);
+    a[0] = fmaf(-bj, x0.x, a[0]); a[1] = fmaf(-bj, x0.y, a[1]);
+    a[2] = fmaf(-bj, x0.z, a[2]); a[3] = fmaf(-bj, x0.w, a[3]);
+    a[4] = fmaf(-bj, x1.x, a[4]); a[5] = fmaf(-bj, x1.y, a[5]);
+    a[6] = fmaf(-bj, x1.z, a[6]); a[7] = fmaf(-bj, x1.w, a[7]);
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = t0 + i;
-      if (t >= t_lo && t < tend) out[(long)(t - t_lo) * B + b] = with_y ? __ldg(yn + t) + a[i] : -a[i];
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int t = t0 + i;
+    if (t >= t_lo && t < t_hi) out[(long)(t - t_lo) * B + b] = with_y ? __ldg(y + (long)n * L.T + t) + a[i] : -a[i];
   }
 }
 
@@ -74,13 +92,9 @@ void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, flo
   const long B = (long)L->N * L->G;
   const int bs = 128;
   const unsigned gb = (unsigned)((B + bs - 1) / bs);
-  // enough (lane-block x time-chunk) CTAs to cover the machine a few times over
-  const int span = t_hi - (t_lo / 8) * 8;
-  int chunks = 1;
-  while ((long)gb * chunks < 148 * 8 && chunks * 8 < span) chunks *= 2;
-  const int t_chunk = ((span + chunks - 1) / chunks + 7) / 8 * 8;
-  chunks = (span + t_chunk - 1) / t_chunk;
-  k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo, t_hi, t_chunk, with_y);
+  const int chunks = (t_hi + 7) / 8 - t_lo / 8;
+  if (chunks <= 0) return;
+  k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo, t_hi, with_y);
 }
 
 void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
@@ -90,90 +104,26 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
 }
 
 template <int S>
-__global__ void __launch_bounds__(128)
-k_kalman(int N, int G, int T, int r, const float* __restrict__ sconst, float* __restrict__ scal,
-         float* __restrict__ resid, float* __restrict__ tape) {
-  const long B = (long)N * G;
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int n = (int)(b / G);
-  float ll, Rb, qlb, qdb;
-  kalman_logp_grad_lane<S>(resid + b, tape + b, B, T, r, scal[0 * B + b], scal[1 * B + b], scal[2 * B + b],
-                           sconst[SC_M0 * N + n], sconst[SC_P0 * N + n], ll, Rb, qlb, qdb);
-  scal[4 * B + b] = ll;
-  scal[5 * B + b] = Rb;
-  scal[6 * B + b] = qlb;
-  scal[7 * B + b] = qdb;
-}
-
-// beta_bar[j][b] = -sum_t rbar[t][b] X[n][j][t]; JT covariates per thread.
-template <int JT>
-__global__ void k_beta_bar(ci_layout L, const float* __restrict__ X, const float* __restrict__ rbar,
-                           float* __restrict__ beta_bar) {
-  const long B = (long)L.N * L.G;
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int n = (int)(b / L.G);
-  const int j0 = blockIdx.y * JT;
-  const float* __restrict__ Xn = X + ((long)n * L.k + j0) * L.Tpad;
-  float acc[JT];
-#pragma unroll
-  for (int i = 0; i < JT; ++i) acc[i] = 0.f;
-  for (int t0 = 0; t0 < L.T; t0 += 4) {
-    float r[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = (t0 + i < L.T) ? rbar[(long)(t0 + i) * B + b] : 0.f;
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj) {
-      if (j0 + jj < L.k) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(Xn + (long)jj * L.Tpad + t0));
-        acc[jj] = fmaf(-r[0], x.x, acc[jj]);
-        acc[jj] = fmaf(-r[1], x.y, acc[jj]);
-        acc[jj] = fmaf(-r[2], x.z, acc[jj]);
-        acc[jj] = fmaf(-r[3], x.w, acc[jj]);
-      }
-    }
-  }
-#pragma unroll
-  for (int jj = 0; jj < JT; ++jj)
-    if (j0 + jj < L.k) beta_bar[(long)(j0 + jj) * B + b] = acc[jj];
-}
-
-__global__ void k_params_backward(int N, int G, int k, int S, const float* __restrict__ sconst,
-                                  const float* __restrict__ u, const float* __restrict__ beta_bar,
-                                  const float* __restrict__ scal, float* __restrict__ logp,
-                                  float* __restrict__ grad) {
-  const long B = (long)N * G;
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int n = (int)(b / G);
-  params_backward_lane(u + b, B, k, S, sconst + n, N, beta_bar + b, scal[5 * B + b], scal[6 * B + b],
-                       scal[7 * B + b], grad + b);
-  logp[b] = scal[3 * B + b] + scal[4 * B + b];
-}
-
-template <int S>
-static void launch_kalman(const ci_layout* L, const ci_data* D, const EvalWs& ws, cudaStream_t st) {
+static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                         const EvalWs& ws, cudaStream_t st) {
   const long B = (long)L->N * L->G;
-  const int bs = 64;
-  k_kalman<S><<<(unsigned)((B + bs - 1) / bs), bs, 0, st>>>(L->N, L->G, L->T, L->r, D->d_sconst, ws.scal,
-                                                             ws.resid, ws.tape);
+  const size_t smem = (size_t)(8 + L->k) * EVAL_THREADS * sizeof(float);
+  auto kern = k_eval<S>;
+  if (smem > 48 * 1024) {
+    if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(*L, D->d_y, D->d_X, D->d_sconst,
+                                                                                      d_u, d_logp, d_grad, ws.tape);
+  return CI_OK;
 }
 
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t st) {
-  const long B = (long)L->N * L->G;
-  const int bs = 128;
-  const unsigned gb = (unsigned)((B + bs - 1) / bs);
-  k_params_forward<<<gb, bs, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, ws.beta, ws.scal);
-  launch_offsets(L, D, ws.beta, ws.resid, 0, L->T, 1, st);
-  CI_DISPATCH_S(L->S, (launch_kalman<S_>(L, D, ws, st)));
-  if (L->k > 0) {
-    constexpr int JT = 8;
-    k_beta_bar<JT><<<dim3(gb, (L->k + JT - 1) / JT), bs, 0, st>>>(*L, D->d_X, ws.resid, ws.beta);
-  }
-  k_params_backward<<<gb, bs, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, ws.beta, ws.scal, d_logp,
-                                       d_grad);
+  int rc = CI_OK;
+  CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_>(L, D, d_u, d_logp, d_grad, ws, st)));
+  if (rc) return rc;
   CI_CHECK_LAUNCH();
   return CI_OK;
 }
@@ -225,14 +175,18 @@ __global__ void k_series_stats(int N, int T, int k, int S, double prior_level_sd
   sconst[SC_PRIOR_CONST * N + n] = (float)c;
 }
 
+// Row-major [N][T+Tf][k] -> chunk-major [N][Tpad/8][k][8], NaN -> 0, zero padding past T+Tf.
 __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, float* __restrict__ Xp) {
   const long total = (long)L.N * L.k * L.Tpad;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int t = (int)(i % L.Tpad);
-  const long nj = i / L.Tpad;
-  const int j = (int)(nj % L.k);
-  const long n = nj / L.k;
+  const int q = (int)(i & 7);
+  long rest = i >> 3;
+  const int j = (int)(rest % L.k);
+  rest /= L.k;
+  const int tc = (int)(rest % (L.Tpad / 8));
+  const long n = rest / (L.Tpad / 8);
+  const int t = tc * 8 + q;
   float v = 0.f;
   if (t < L.T + L.Tf) {
     v = Xrm[(n * (L.T + L.Tf) + t) * L.k + j];

@@ -39,7 +39,8 @@ struct LaneScalars {
 
 // u, beta: element stride `ld`.  sc: pointer to this series' constants with field stride `scld`.
 CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int k, int S,
-                                      const float* __restrict__ sc, long scld, float* __restrict__ beta) {
+                                      const float* __restrict__ sc, long scld, float* __restrict__ beta,
+                                      long ldb) {
   const float sd = sc[SC_SD * scld];
   LaneScalars o;
   const float u0 = u[0], u1 = u[ld];
@@ -63,7 +64,7 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
       const float a = ulsv[(long)j * ld], b = ulsn[(long)j * ld], wn = uwn[(long)j * ld];
       const float lsv = softplus(a), lsn = softplus(b);
       lp += -1.5f * logf(lsv) - 0.5f / lsv - 0.5f * lsn * lsn - 0.5f * wn * wn + log_sigmoid(a) + log_sigmoid(b);
-      beta[(long)j * ld] = wn * lsn * sqrtf(lsv) * G;
+      beta[(long)j * ldb] = wn * lsn * sqrtf(lsv) * G;
     }
   }
   if (S > 1) {
@@ -80,10 +81,10 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
 }
 
 // grad[i] = d/du_i [ log prior + log-det + log-lik ], given the filter adjoints
-// (Rb, qlb, qdb) and beta_bar = dloglik/dbeta (stride ld).
+// (Rb, qlb, qdb) and beta_bar = dloglik/dbeta (stride ldb).
 CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int S,
                                 const float* __restrict__ sc, long scld,
-                                const float* __restrict__ beta_bar, float Rb, float qlb, float qdb,
+                                const float* __restrict__ beta_bar, long ldb, float Rb, float qlb, float qdb,
                                 float* __restrict__ grad) {
   const float sd = sc[SC_SD * scld];
   {
@@ -115,7 +116,7 @@ CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int
       const float lsv = softplus(a), lsn = softplus(b);
       const float sq = sqrtf(lsv);
       const float l = lsn * sq;
-      const float bb = beta_bar[(long)j * ld];
+      const float bb = beta_bar[(long)j * ldb];
       dG = fmaf(bb, wn * l, dG);
       gwn[(long)j * ld] = bb * l * G - wn;
       const float dl = bb * wn * G;

@@ -2,7 +2,7 @@
 
 Layout in HBM (float32, lane = fastest axis of every per-lane array):
     y      [N][T]          observed series (NaN = missing)
-    X      [N][k][Tpad]    packed design matrix, time contiguous (16-byte loads of 4 steps)
+    X      [N][Tpad/8][k][8] chunk-major design matrix (8 steps of a covariate = 32 contiguous bytes)
     sconst [8][N]          per-series constants (mean, sd, m0, P0, prior hyper-parameters)
     u/grad [P][B]          unconstrained parameters / gradient, B = N * G lanes
 """
@@ -37,7 +37,7 @@ class DeviceBatch:
             assert X.shape[0] == self.N and X.shape[1] == self.T + self.Tf, \
                 f'design matrix must be [N, T+Tf, k], got {tuple(X.shape)}'
             self.k = X.shape[2]
-        self.Tpad = (self.T + self.Tf + 3) // 4 * 4
+        self.Tpad = (self.T + self.Tf + 7) // 8 * 8
         self.P = nt.num_params(self.k, self.S)
         self.sconst = torch.empty((8, self.N), dtype=torch.float32, device=self.device)
         L = self.layout(1)
@@ -46,7 +46,7 @@ class DeviceBatch:
                                               nt.ptr(self.sconst), nt.stream_ptr()), 'ci_series_stats')
             if self.k > 0:
                 Xrm = X.to(self.device, torch.float32).contiguous()
-                self.X = torch.empty((self.N, self.k, self.Tpad), dtype=torch.float32, device=self.device)
+                self.X = torch.empty((self.N, self.Tpad // 8, self.k, 8), dtype=torch.float32, device=self.device)
                 nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.X), nt.stream_ptr()),
                          'ci_pack_design')
                 # stream-ordered: Xrm may be released once the pack kernel has been enqueued
@@ -225,7 +225,7 @@ class DeviceBatch:
 
 
 def _layout_for(N, T, Tf):
-    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 3) // 4 * 4)
+    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 7) // 8 * 8)
 
 
 def reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):
