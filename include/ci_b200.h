@@ -45,13 +45,13 @@ typedef struct ci_layout {
   int32_t k;    /* covariates (0 = no regression component; model.py:298) */
   int32_t S;    /* nseasons (1 = no seasonal component; model.py:310) */
   int32_t r;    /* season_duration (model.py:313) */
-  int32_t Tpad; /* padded length of the packed design matrix: multiple of 8, >= T + Tf */
+  int32_t Tpad; /* padded length of the packed design matrix: multiple of 4, >= T + Tf */
 } ci_layout;
 
 /* Caller-owned device inputs shared by every call on one batch of series. */
 typedef struct ci_data {
   const float* d_y;      /* [N][T]        observed series, NaN = missing step            */
-  const float* d_X;      /* [N][Tpad/8][k][8] chunk-major design matrix (ci_pack_design) */
+  const float* d_X;      /* [N][Tpad/4][k+1][4] chunk-major covariates + y (ci_pack_design) */
   const float* d_sconst; /* [8][N]        per-series constants (see ci_series_stats)     */
 } ci_data;
 
@@ -68,10 +68,13 @@ int ci_num_params(int32_t k, int32_t S);
 int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, float* d_sconst,
                     void* stream);
 
-/* Row-major covariates [N][T+Tf][k] -> chunk-major [N][Tpad/8][k][8] (8 steps of one covariate
- * contiguous, NaN -> 0, zero padded).
+/* Row-major covariates [N][T+Tf][k] and the series [N][T] -> chunk-major [N][Tpad/4][k+1][4]:
+ * 4 consecutive steps of one covariate are 16 contiguous bytes, row k of every chunk holds y
+ * itself (NaN -> 0 in covariates, zero padded; NaN in y = missing).  Required for every layout,
+ * also k = 0.  d_X_rowmajor may be NULL when k = 0.
  * Replaces: causalimpact/model.py:303-308 (concat(pre, post).astype(float32).fillna(0)). */
-int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, float* d_X_packed, void* stream);
+int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d_y, float* d_XY_packed,
+                   void* stream);
 
 /* ---- K1-K3: joint log-prob + gradient in unconstrained space ------------------------------
  * Replaces: `model.joint_log_prob(observed_time_series)` + TF autodiff, causalimpact/model.py:375-377

@@ -48,14 +48,17 @@ def synth_problem(N, T, Tf, k, S, r=1, seed=0, nan_frac=0.0, standardize=True):
     return y[:, :T].copy(), y[:, T:].copy(), X
 
 
-def pack_X(X, Tpad=None):
-    """[N, Ttot, k] -> chunk-major [N, Tpad/8, k, 8], zero padded to a multiple of 8 steps."""
+def pack_X(X, y, Tpad=None):
+    """X [N, Ttot, k], y [N, T] -> chunk-major XY [N, Tpad/4, k+1, 4] (row k = y, NaN past T)."""
     N, Tt, k = X.shape
+    T = y.shape[1]
     if Tpad is None:
-        Tpad = (Tt + 7) // 8 * 8
-    buf = np.zeros((N, Tpad, k), dtype=np.float32)
-    buf[:, :Tt, :] = X
-    out = np.ascontiguousarray(buf.reshape(N, Tpad // 8, 8, k).transpose(0, 1, 3, 2))
+        Tpad = (Tt + 3) // 4 * 4
+    buf = np.zeros((N, Tpad, k + 1), dtype=np.float32)
+    buf[:, :Tt, :k] = X
+    buf[:, :, k] = np.nan
+    buf[:, :T, k] = y
+    out = np.ascontiguousarray(buf.reshape(N, Tpad // 4, 4, k + 1).transpose(0, 1, 3, 2))
     return out, Tpad
 
 
@@ -114,18 +117,18 @@ def fptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def shim_logp_grad(L, y, Xp, Tpad, sconst, u_pb, G):
-    """u_pb: [P, B] float32 (lane fastest).  Returns logp[B], grad[P, B]."""
+def shim_logp_grad(L, XY, Tpad, sconst, u_pb, G):
+    """XY: chunk-major [N, Tpad/4, k+1, 4]; u_pb: [P, B] float32 (lane fastest).
+    Returns logp[B], grad[P, B]."""
     lib = host_shim()
-    N = y.shape[0]
+    N = XY.shape[0]
     B = N * G
     logp = np.zeros(B, dtype=np.float32)
     grad = np.zeros((L.P, B), dtype=np.float32)
-    y = np.ascontiguousarray(y, dtype=np.float32)
-    Xp = np.ascontiguousarray(Xp, dtype=np.float32)
+    XY = np.ascontiguousarray(XY, dtype=np.float32)
     sconst = np.ascontiguousarray(sconst, dtype=np.float32)
     u_pb = np.ascontiguousarray(u_pb, dtype=np.float32)
-    rc = lib.shim_logp_grad(N, G, L.T, L.k, L.S, L.r, fptr(y), fptr(Xp), Tpad, fptr(sconst), fptr(u_pb),
-                            fptr(logp), fptr(grad))
+    rc = lib.shim_logp_grad(N, G, L.T, L.k, L.S, L.r, fptr(XY), Tpad, fptr(sconst), fptr(u_pb), fptr(logp),
+                            fptr(grad))
     assert rc == 0, rc
     return logp, grad

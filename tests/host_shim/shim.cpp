@@ -11,20 +11,22 @@
 using namespace ci;
 
 template <int S>
-static void lane_eval(const float* u, long B, const float* sc, int N, const float* yn, const float* Xn, int T, int k,
-                      int r, float* sb, float* sr, float* tape, float* logp, float* grad) {
-  eval_lane<S>(u, B, sc, N, yn, Xn, T, k, r, sb, 1, sr, 4, tape, 1, logp, grad);
+static void lane_eval(const float* u, long B, const float* sc, int N, const float* XYn, int T, int k, int r,
+                      float* sb, float* sr, float* tape, float* logp, float* grad) {
+  XDirect xs{XYn, (k + 1) * CI_TC};
+  eval_lane<S>(u, B, sc, N, xs, T, k, r, sb, 1, sr, tape, 1, logp, grad);
 }
 
 // Runs ci::eval_lane -- the exact per-lane function the CUDA kernel k_eval executes -- for every lane.
-extern "C" int shim_logp_grad(int N, int G, int T, int k, int S, int r, const float* y, const float* X,
-                              int Tpad, const float* sconst, const float* u, float* logp, float* grad) {
+// XY: chunk-major [N][Tpad/4][k+1][4] (row k = y).
+extern "C" int shim_logp_grad(int N, int G, int T, int k, int S, int r, const float* XY, int Tpad,
+                              const float* sconst, const float* u, float* logp, float* grad) {
   const long B = (long)N * G;
-  std::vector<float> sb((size_t)(k > 0 ? k : 1)), sr(8), tape((size_t)T * (S + 2));
+  std::vector<float> sb((size_t)(k > 0 ? k : 1)), sr(4), tape((size_t)T * (S + 1));
   for (long b = 0; b < B; ++b) {
     const int n = (int)(b / G);
-    CI_DISPATCH_S(S, (lane_eval<S_>(u + b, B, sconst + n, N, y + (long)n * T, X + (long)n * k * Tpad, T, k, r,
-                                    sb.data(), sr.data(), tape.data(), logp + b, grad + b)));
+    CI_DISPATCH_S(S, (lane_eval<S_>(u + b, B, sconst + n, N, XY + (long)n * (k + 1) * Tpad, T, k, r, sb.data(),
+                                    sr.data(), tape.data(), logp + b, grad + b)));
   }
   return 0;
 }

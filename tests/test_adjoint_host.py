@@ -29,13 +29,13 @@ def test_lane_logp_grad_matches_oracle(S, r, k, T, nan_frac):
     y, _, X = synth_problem(N, T, Tf, k, S, r, seed=S * 100 + k, nan_frac=nan_frac)
     prob = O.Problem.build(y, X, L, dtype=torch.float64)
     sc = sconst_from_oracle(prob)
-    Xp, Tpad = pack_X(X)
+    XY, Tpad = pack_X(X, y)
     rng = np.random.default_rng(1)
     B = N * G
     u = (rng.normal(size=(L.P, B)) * 0.7).astype(np.float32)
     u[0] -= 1.0
     u[1] -= 2.0
-    lp, g = shim_logp_grad(L, y, Xp, Tpad, sc, u, G)
+    lp, g = shim_logp_grad(L, XY, Tpad, sc, u, G)
     series = torch.arange(B) // G
     lpo, go = O.target_log_prob_and_grad(prob, torch.tensor(u.T.astype(np.float64)), series)
     lpo, go = lpo.numpy(), go.numpy().T

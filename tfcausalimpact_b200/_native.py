@@ -66,7 +66,7 @@ def stream_ptr():
 
 def make_layout(N, G, T, Tf, k, S=1, r=1, Tpad=None):
     if Tpad is None:
-        Tpad = (T + Tf + 7) // 8 * 8
+        Tpad = (T + Tf + 3) // 4 * 4
     return CiLayout(N, G, T, Tf, k, S, r, Tpad)
 
 

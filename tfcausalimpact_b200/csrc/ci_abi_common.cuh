@@ -35,8 +35,8 @@ inline int check_layout(const ci_layout* L) {
   if (L->N < 1 || L->G < 1 || L->T < 1 || L->Tf < 0 || L->k < 0 || L->S < 1 || L->r < 1)
     return fail(CI_ERR_INVALID_ARGUMENT, "layout has a non-positive dimension");
   if (L->S == 1 && L->r != 1) return fail(CI_ERR_INVALID_ARGUMENT, "season_duration > 1 needs nseasons > 1");
-  if (L->k > 0 && (L->Tpad % 8 != 0 || L->Tpad < L->T + L->Tf))
-    return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 8 and >= T + Tf");
+  if (L->Tpad % 4 != 0 || L->Tpad < L->T + L->Tf)
+    return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 4 and >= T + Tf");
   return CI_OK;
 }
 
@@ -56,11 +56,11 @@ struct Carver {
 
 // Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
-  float* tape;   // [T][S+2][B]
+  float* tape;   // [T][S+1][B]  (g_0..g_{S-1}, v)
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   const size_t B = (size_t)L->N * L->G;
-  const size_t nt = (size_t)L->T * (L->S + 2) * B;
+  const size_t nt = (size_t)L->T * (L->S + 1) * B;
   if (ws && c) ws->tape = c->floats(nt);
   return align_up(nt * 4, 256);
 }

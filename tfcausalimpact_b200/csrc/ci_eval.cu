@@ -1,14 +1,18 @@
 // K1-K3: joint log-prob + gradient of the fixed-layout structural time-series model, ONE kernel:
-//   k_eval<S>  -- thread per (series, chain[, sample]) lane; per lane (ci_eval_lane.cuh):
+//   k_eval<S, STAGED>  -- thread per (series, chain[, sample]) lane; per lane (ci_eval_lane.cuh):
 //        u -> sigma^2's, beta (shared-memory column)                                [K3 forward]
-//        per 8-step chunk: r = y - mean - X beta (two 16-byte loads per covariate), 8 Kalman steps,
-//        tape (g, s, v) -> HBM                                                       [K2 + K1 forward]
+//        per 4-step chunk: r = y - mean - X beta from the TMA-staged chunk, 4 Kalman steps,
+//        tape (g, v) -> HBM                                                          [K2 + K1 forward]
 //        reverse sweep with software-pipelined tape reads, beta_bar += rbar X per chunk
 //        VJP through horseshoe / softplus / sqrt + priors -> grad                   [K1-K3 reverse]
-// Lanes are the fastest axis of every per-lane array ([P][B] parameters, [T][S+2][B] tape), so each
-// warp access is one 128 B line; the design matrix is chunk-major [N][Tpad/8][k][8] so the lanes of a
-// CTA stream contiguous 32k-byte runs.  Mean, packed covariance and their adjoints stay in
-// registers for the whole evaluation; nothing but the tape is spilled to HBM.
+// Lanes are the fastest axis of every per-lane array ([P][B] parameters, [T][S+1][B] tape), so each
+// warp access is one 128 B line.  The design matrix (with y as its last row) is chunk-major
+// [N][Tpad/4][k+1][4]: the run a (series, chunk) needs is 16(k+1) contiguous bytes, fetched by ONE
+// cp.async.bulk (TMA) per series into the CTA's staging buffer and signalled on an mbarrier; the
+// copy of chunk c+1 is issued as soon as every lane has consumed chunk c and lands while the 4 filter
+// steps of chunk c run, so the regression loops never wait on HBM.  All C chains of a series sit in
+// the same CTA and read the staged chunk by shared-memory broadcast.  Mean, packed covariance and
+// their adjoints stay in registers for the whole evaluation; nothing but the tape is spilled to HBM.
 //   k_params_forward / k_offsets -- u -> beta / offsets for the predictive path (ci_predict.cu).
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
@@ -22,22 +26,108 @@ char* last_error_buf() {
 
 constexpr int EVAL_THREADS = 64;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA-staged policy: the CTA's series share one staging buffer filled by cp.async.bulk.
+struct XStaged {
+  const float* lane_x;   // this lane's series slice of the staging buffer (shared memory)
+  uint32_t sx_addr;      // staging buffer base, shared-space address
+  uint32_t bar;          // mbarrier, shared-space address
+  uint32_t parity;
+  const float* gsrc;     // XY of the CTA's first series (global)
+  long series_stride;    // floats between consecutive series
+  int stride;            // floats per chunk = (k + 1) * CI_TC
+  int ns;                // series staged by this CTA
+
+  __device__ __forceinline__ void issue(int tc) const {   // one elected thread
+    const uint32_t bytes = (uint32_t)stride * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)ns)
+                 : "memory");
+    const float* src = gsrc + (long)tc * stride;
+    for (int s = 0; s < ns; ++s)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       sx_addr + (uint32_t)s * bytes),
+                   "l"(src + (long)s * series_stride), "r"(bytes), "r"(bar)
+                   : "memory");
+  }
+  __device__ __forceinline__ void acquire() {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    } while (!ok);
+    parity ^= 1u;
+  }
+  __device__ __forceinline__ void release(int next_tc) const {
+    // every lane of the CTA has consumed the staged chunk.  Non-.aligned barrier: the padding lanes
+    // of the last CTA arrive from idle_lane(), i.e. from a different program point of the same warp.
+    asm volatile("barrier.sync 0;" ::: "memory");
+    if (threadIdx.x == 0 && next_tc >= 0) issue(next_tc);
+  }
+  __device__ __forceinline__ const float* chunk(int) const { return lane_x; }
+  __device__ __forceinline__ f4 load(const float* p) const {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    return f4{v.x, v.y, v.z, v.w};
+  }
+};
+
+// Series one CTA of EVAL_THREADS lanes can touch (lanes of a series are contiguous).
+__host__ __device__ inline int staged_series_max(int G) {
+  const int a = (EVAL_THREADS + G - 2) / G + 1;
+  return a < EVAL_THREADS ? a : EVAL_THREADS;
+}
+
 // Registers are capped so that >= 640 lanes stay resident per SM for the small latent sizes
 // (S <= 7 -> <= 102 registers): 148 SMs x 640 = 94,720 lanes, i.e. the 80,000 lanes of the headline
 // workload run as ONE wave (the run time of a lane is fixed by its T sequential steps).
-template <int S>
+template <int S, bool STAGED>
 __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
-k_eval(ci_layout L, const float* __restrict__ y, const float* __restrict__ X, const float* __restrict__ sconst,
-       const float* __restrict__ u, float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
+k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+       float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
   const long B = (long)L.N * L.G;
-  const long b = (long)blockIdx.x * EVAL_THREADS + threadIdx.x;
-  if (b >= B) return;
-  const int n = (int)(b / L.G);
-  float* sr = smem + threadIdx.x * 4;                     // [2][EVAL_THREADS][4]
-  float* sb = smem + 8 * EVAL_THREADS + threadIdx.x;      // [k][EVAL_THREADS]
-  eval_lane<S>(u + b, B, sconst + n, L.N, y + (long)n * L.T, X + (long)n * L.k * L.Tpad, L.T, L.k, L.r, sb,
-               EVAL_THREADS, sr, 4 * EVAL_THREADS, tape + b, B, logp + b, grad + b);
+  const long b0 = (long)blockIdx.x * EVAL_THREADS;
+  const long b = b0 + threadIdx.x;
+  const bool valid = b < B;
+  const int n = (int)((valid ? b : B - 1) / L.G);
+  const int stride = (L.k + 1) * CI_TC;
+  const long series_stride = (long)(L.Tpad / CI_TC) * stride;
+  float* sr = smem + threadIdx.x * 4;                     // [EVAL_THREADS][4]
+  float* sb = smem + 4 * EVAL_THREADS + threadIdx.x;      // [k][EVAL_THREADS]
+  if (STAGED) {
+    float* sx = smem + (4 + L.k) * EVAL_THREADS;          // [ns][stride]
+    const int n_lo = (int)(b0 / L.G);
+    const long b_last = (b0 + EVAL_THREADS - 1 < B ? b0 + EVAL_THREADS - 1 : B - 1);
+    const int ns = (int)(b_last / L.G) - n_lo + 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sx + (long)staged_series_max(L.G) * stride);
+    XStaged xs;
+    xs.lane_x = sx + (long)(n - n_lo) * stride;
+    xs.sx_addr = smem_u32(sx);
+    xs.bar = smem_u32(bar);
+    xs.parity = 0u;
+    xs.gsrc = XY + (long)n_lo * series_stride;
+    xs.series_stride = series_stride;
+    xs.stride = stride;
+    xs.ns = ns;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs.bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) xs.issue(0);
+    if (valid)
+      eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+    else
+      idle_lane(xs, L.T);
+  } else {
+    if (!valid) return;
+    XDirect xs{XY + (long)n * series_stride, stride};
+    eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+  }
 }
 
 __global__ void k_params_forward(int N, int G, int k, int S, const float* __restrict__ sconst,
@@ -56,32 +146,32 @@ __global__ void k_params_forward(int N, int G, int k, int S, const float* __rest
 
 // out[t - t_lo][b] for t in [t_lo, t_hi):  with_y ? y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]
 //                                                 : mean[n] + sum_j beta[j][b] X[n][j][t];
-// one (lane, 8-step chunk) per thread.  Used by the predictive path only.
-__global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ X,
+// one (lane, 4-step chunk) per thread.  Used by the predictive path only.
+__global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ XY,
                           const float* __restrict__ sconst, const float* __restrict__ beta,
                           float* __restrict__ out, int t_lo, int t_hi, int with_y) {
   const long B = (long)L.N * L.G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / L.G);
-  const int tc = t_lo / 8 + blockIdx.y;
-  const int t0 = tc * 8;
+  const int tc = t_lo / CI_TC + blockIdx.y;
+  const int t0 = tc * CI_TC;
   if (t0 >= t_hi) return;
   const float mean = sconst[SC_MEAN * L.N + n];
-  float a[8];
+  float a[CI_TC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = -mean;
-  const float* __restrict__ xp = X + ((long)n * (L.Tpad / 8) + tc) * L.k * 8;
+  for (int i = 0; i < CI_TC; ++i) a[i] = -mean;
+  const int stride = (L.k + 1) * CI_TC;
+  XDirect xs{XY + (long)n * (L.Tpad / CI_TC) * stride, stride};
+  const float* __restrict__ xp = xs.chunk(tc);
   for (int j = 0; j < L.k; ++j) {
     const float bj = beta[(long)j * B + b];
-    const f4 x0 = load4(xp + j * 8), x1 = load4(xp + j * 8 + 4);
-    a[0] = fmaf(-bj, x0.x, a[0]); a[1] = fmaf(-bj, x0.y, a[1]);
-    a[2] = fmaf(-bj, x0.z, a[2]); a[3] = fmaf(-bj, x0.w, a[3]);
-    a[4] = fmaf(-bj, x1.x, a[4]); a[5] = fmaf(-bj, x1.y, a[5]);
-    a[6] = fmaf(-bj, x1.z, a[6]); a[7] = fmaf(-bj, x1.w, a[7]);
+    const f4 x = xs.load(xp + j * CI_TC);
+    a[0] = fmaf(-bj, x.x, a[0]); a[1] = fmaf(-bj, x.y, a[1]);
+    a[2] = fmaf(-bj, x.z, a[2]); a[3] = fmaf(-bj, x.w, a[3]);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CI_TC; ++i) {
     const int t = t0 + i;
     if (t >= t_lo && t < t_hi) out[(long)(t - t_lo) * B + b] = with_y ? __ldg(y + (long)n * L.T + t) + a[i] : -a[i];
   }
@@ -92,7 +182,7 @@ void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, flo
   const long B = (long)L->N * L->G;
   const int bs = 128;
   const unsigned gb = (unsigned)((B + bs - 1) / bs);
-  const int chunks = (t_hi + 7) / 8 - t_lo / 8;
+  const int chunks = (t_hi + CI_TC - 1) / CI_TC - t_lo / CI_TC;
   if (chunks <= 0) return;
   k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo, t_hi, with_y);
 }
@@ -103,26 +193,35 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
   k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, beta, scal);
 }
 
-template <int S>
+template <int S, bool STAGED>
 static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                          const EvalWs& ws, cudaStream_t st) {
   const long B = (long)L->N * L->G;
-  const size_t smem = (size_t)(8 + L->k) * EVAL_THREADS * sizeof(float);
-  auto kern = k_eval<S>;
+  size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
+  if (STAGED) smem += (size_t)staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 16;
+  auto kern = k_eval<S, STAGED>;
   if (smem > 48 * 1024) {
     if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(*L, D->d_y, D->d_X, D->d_sconst,
-                                                                                      d_u, d_logp, d_grad, ws.tape);
+  kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
+                                                                                      d_logp, d_grad, ws.tape);
   return CI_OK;
 }
+
+// Staging pays when several lanes share a series (the staged run is then smaller than the beta
+// column it sits beside); single-lane-per-series calls read X directly.
+static bool use_staging(const ci_layout* L) { return L->G >= 4 && L->k >= 4; }
 
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t st) {
   int rc = CI_OK;
-  CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_>(L, D, d_u, d_logp, d_grad, ws, st)));
+  if (use_staging(L)) {
+    CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true>(L, D, d_u, d_logp, d_grad, ws, st)));
+  } else {
+    CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false>(L, D, d_u, d_logp, d_grad, ws, st)));
+  }
   if (rc) return rc;
   CI_CHECK_LAUNCH();
   return CI_OK;
@@ -175,24 +274,31 @@ __global__ void k_series_stats(int N, int T, int k, int S, double prior_level_sd
   sconst[SC_PRIOR_CONST * N + n] = (float)c;
 }
 
-// Row-major [N][T+Tf][k] -> chunk-major [N][Tpad/8][k][8], NaN -> 0, zero padding past T+Tf.
-__global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, float* __restrict__ Xp) {
-  const long total = (long)L.N * L.k * L.Tpad;
+// Row-major X [N][T+Tf][k] + y [N][T] -> chunk-major XY [N][Tpad/4][k+1][4]: rows 0..k-1 covariates
+// (NaN -> 0, zero padding past T+Tf), row k the observed series (NaN = missing / past T).
+__global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const float* __restrict__ y,
+                              float* __restrict__ XY) {
+  const long total = (long)L.N * (L.k + 1) * L.Tpad;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int q = (int)(i & 7);
-  long rest = i >> 3;
-  const int j = (int)(rest % L.k);
-  rest /= L.k;
-  const int tc = (int)(rest % (L.Tpad / 8));
-  const long n = rest / (L.Tpad / 8);
-  const int t = tc * 8 + q;
-  float v = 0.f;
-  if (t < L.T + L.Tf) {
-    v = Xrm[(n * (L.T + L.Tf) + t) * L.k + j];
-    if (!(v == v)) v = 0.f;
+  const int q = (int)(i % CI_TC);
+  long rest = i / CI_TC;
+  const int j = (int)(rest % (L.k + 1));
+  rest /= (L.k + 1);
+  const int tc = (int)(rest % (L.Tpad / CI_TC));
+  const long n = rest / (L.Tpad / CI_TC);
+  const int t = tc * CI_TC + q;
+  float v;
+  if (j < L.k) {
+    v = 0.f;
+    if (t < L.T + L.Tf) {
+      v = Xrm[(n * (L.T + L.Tf) + t) * L.k + j];
+      if (!(v == v)) v = 0.f;
+    }
+  } else {
+    v = t < L.T ? y[n * L.T + t] : nanf("");
   }
-  Xp[i] = v;
+  XY[i] = v;
 }
 
 __global__ void k_constrain(int N, int G, int k, int S, const float* __restrict__ sconst,
@@ -224,12 +330,11 @@ int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, 
   return CI_OK;
 }
 
-int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, float* d_X_packed, void* stream) {
+int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d_y, float* d_XY_packed, void* stream) {
   if (int e = check_layout(L)) return e;
-  if (L->k == 0) return CI_OK;
-  CI_CHECK_ARG(d_X_rowmajor && d_X_packed, "NULL pointer");
-  const long total = (long)L->N * L->k * L->Tpad;
-  k_pack_design<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*L, d_X_rowmajor, d_X_packed);
+  CI_CHECK_ARG((L->k == 0 || d_X_rowmajor) && d_y && d_XY_packed, "NULL pointer");
+  const long total = (long)L->N * (L->k + 1) * L->Tpad;
+  k_pack_design<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*L, d_X_rowmajor, d_y, d_XY_packed);
   CI_CHECK_LAUNCH();
   return CI_OK;
 }
@@ -242,7 +347,7 @@ size_t ci_eval_workspace_bytes(const ci_layout* L) {
 int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                         void* d_workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_layout(L)) return e;
-  CI_CHECK_ARG(D && D->d_y && D->d_sconst && (L->k == 0 || D->d_X), "NULL data pointer");
+  CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_logp && d_grad && d_workspace, "NULL pointer");
   if (L->S > CI_MAX_REG_S) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_eval_workspace_bytes(L))

@@ -1,22 +1,30 @@
 // One complete joint log-prob + gradient evaluation for one (series, chain[, sample]) lane:
 //   u -> (sigma^2's, beta, prior + log-det)                                     [K3 forward]
-//   r_t = y_t - mean - X_t . beta, Kalman filter, tape (g_t, s_t, v_t)           [K2 + K1 forward]
+//   r_t = y_t - mean - X_t . beta, Kalman filter, tape (g_t, v_t)                [K2 + K1 forward]
 //   reverse-time adjoint sweep -> dL/dr_t -> beta_bar = -sum_t rbar_t X_t        [K1 + K2 reverse]
 //   VJP through horseshoe / softplus / sqrt + prior gradient                     [K3 reverse]
 // in ONE pass per direction over the series.  Nothing but the tape leaves the thread: beta /
-// beta_bar live in a per-lane scratch column (shared memory on the device), the 8 residuals of the
-// current time chunk in a second one, mean / covariance / adjoints in registers.
+// beta_bar live in a per-lane scratch column (shared memory on the device), the CI_TC residuals of
+// the current time chunk in a second one, mean / covariance / adjoints in registers.
 //
-// Design matrix layout ("chunk-major"): X[n][tc][j][8], tc = t / 8 -- the k covariates of 8
-// consecutive time steps are one contiguous 32*k-byte run, so a lane pulls 8 steps of one covariate
-// with two 16-byte loads and a CTA streams whole 128-byte lines.
+// Design matrix layout ("chunk-major"): XY[n][tc][j][CI_TC], tc = t / CI_TC, j = 0..k with row k
+// holding the observed series y itself (NaN = missing) -- the k covariates and y of CI_TC consecutive
+// steps are one contiguous 16(k+1)-byte run, which the CUDA kernel stages into shared memory with one
+// TMA bulk copy per (series, chunk) while the previous chunk's filter steps run.
 //
-// `__host__ __device__`: the TEST-ONLY host shim (tests/host_shim) runs exactly this function on the
-// CPU against the oracle.  Math: SURVEY.md Appendix A.2-A.5.
+// Tape entry per step: g_0..g_{S-1}, v  (s = g_0 + g_1 + R is recomputed; v = NaN marks a masked
+// step).
+//
+// The function is templated on an X-source policy (`acquire` / `chunk` / `release`) so that the
+// TEST-ONLY host shim (tests/host_shim) runs exactly this arithmetic on the CPU against the oracle,
+// and the kernel can choose between TMA-staged shared memory and direct global loads.
+// Math: SURVEY.md Appendix A.2-A.5.
 #pragma once
 #include "ci_core.cuh"
 #include "ci_kalman.cuh"
 #include "ci_params.cuh"
+
+#define CI_TC 4  // time steps per chunk
 
 namespace ci {
 
@@ -24,74 +32,70 @@ struct f4 {
   float x, y, z, w;
 };
 
-CI_HD f4 load4(const float* p) {
+// Direct policy: the lane reads its series' chunks straight from (global) memory.
+struct XDirect {
+  const float* base;  // XY[n]
+  int stride;         // floats per chunk = (k + 1) * CI_TC
+  CI_HD void acquire() {}
+  CI_HD void release(int /*next_tc*/) {}
+  CI_HD const float* chunk(int tc) const { return base + (long)tc * stride; }
+  CI_HD f4 load(const float* p) const {
 #if defined(__CUDA_ARCH__)
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-  return f4{v.x, v.y, v.z, v.w};
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return f4{v.x, v.y, v.z, v.w};
 #else
-  return f4{p[0], p[1], p[2], p[3]};
+    return f4{p[0], p[1], p[2], p[3]};
 #endif
-}
-CI_HD float load1(const float* p) {
-#if defined(__CUDA_ARCH__)
-  return __ldg(p);
-#else
-  return *p;
-#endif
-}
+  }
+};
 
 // sb   : per-lane scratch column for beta / beta_bar, element j at sb[j * sbld]
-// sr   : per-lane scratch for the 8 residuals of a chunk: element i at sr[(i >> 2) * srld + (i & 3)]
-// tape : [T][S+2] with element stride ldt
+// sr   : per-lane scratch for the CI_TC residuals of a chunk (sr[0..3], 16-byte aligned on device)
+// tape : [T][S+1] with element stride ldt
 // u, grad : [P] with element stride ld
-template <int S>
-CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld,
-                     const float* __restrict__ yn, const float* __restrict__ Xn, int T, int k, int r_dur,
-                     float* __restrict__ sb, int sbld, float* __restrict__ sr, int srld,
-                     float* __restrict__ tape, long ldt, float* __restrict__ logp_out,
-                     float* __restrict__ grad) {
-  constexpr int TW = S + 2;
+template <int S, class XS>
+CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs, int T,
+                     int k, int r_dur, float* __restrict__ sb, int sbld, float* __restrict__ sr,
+                     float* __restrict__ tape, long ldt, float* __restrict__ logp_out, float* __restrict__ grad) {
+  constexpr int TW = S + 1;
   const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, sbld);
   const float R = ls.R, ql = ls.ql, qd = ls.qd;
   const float mean = sc[SC_MEAN * scld];
-  const int nchunk = (T + 7) >> 3;
+  const int nchunk = (T + CI_TC - 1) / CI_TC;
 
-  // ---- forward: residual chunk (regression GEMV) + 8 filter steps ------------------------------
+  // ---- forward: residual chunk (regression GEMV) + CI_TC filter steps --------------------------
   KState<S> ks;
   kf_init<S>(ks, sc[SC_M0 * scld], sc[SC_P0 * scld]);
   float acc = 0.f, comp = 0.f;  // compensated sum of log s + v^2/s
   int nobs = 0;
   int phase = 0;
   for (int tc = 0; tc < nchunk; ++tc) {
-    const int t0 = tc << 3;
-    const int nstep = (T - t0) < 8 ? (T - t0) : 8;
+    const int t0 = tc * CI_TC;
+    const int nstep = (T - t0) < CI_TC ? (T - t0) : CI_TC;
+    xs.acquire();
     {
-      float r[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = (i < nstep ? load1(yn + t0 + i) : 0.f) - mean;
-      const float* __restrict__ xp = Xn + (long)tc * k * 8;
-#pragma unroll 4
+      const float* __restrict__ xp = xs.chunk(tc);
+      const f4 yv = xs.load(xp + k * CI_TC);
+      float r0 = yv.x - mean, r1 = yv.y - mean, r2 = yv.z - mean, r3 = yv.w - mean;
+#pragma unroll 5
       for (int j = 0; j < k; ++j) {
         const float bj = sb[j * sbld];
-        const f4 x0 = load4(xp + j * 8), x1 = load4(xp + j * 8 + 4);
-        r[0] = fmaf(-bj, x0.x, r[0]); r[1] = fmaf(-bj, x0.y, r[1]);
-        r[2] = fmaf(-bj, x0.z, r[2]); r[3] = fmaf(-bj, x0.w, r[3]);
-        r[4] = fmaf(-bj, x1.x, r[4]); r[5] = fmaf(-bj, x1.y, r[5]);
-        r[6] = fmaf(-bj, x1.z, r[6]); r[7] = fmaf(-bj, x1.w, r[7]);
+        const f4 x = xs.load(xp + j * CI_TC);
+        r0 = fmaf(-bj, x.x, r0); r1 = fmaf(-bj, x.y, r1);
+        r2 = fmaf(-bj, x.z, r2); r3 = fmaf(-bj, x.w, r3);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sr[(i >> 2) * srld + (i & 3)] = r[i];
+      sr[0] = r0; sr[1] = r1; sr[2] = r2; sr[3] = r3;
     }
+    xs.release(tc + 1 < nchunk ? tc + 1 : -1);   // chunk tc+1 streams in while the steps below run
     for (int i = 0; i < nstep; ++i) {
-      const float r = sr[(i >> 2) * srld + (i & 3)];
+      const float r = sr[i];
       float* tp = tape + (long)(t0 + i) * TW * ldt;
       if (r == r) {
         float g[S], s, v, is;
         kf_update<S>(ks, r, R, g, s, v, is);
 #pragma unroll
         for (int q = 0; q < S; ++q) tp[(long)q * ldt] = g[q];
-        tp[(long)S * ldt] = s;
-        tp[(long)(S + 1) * ldt] = v;
+        tp[(long)S * ldt] = v;
         const float term = logf(s) + v * v * is;
         const float yk = term - comp;
         const float tk = acc + yk;
@@ -100,7 +104,8 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
         ++nobs;
       } else {
 #pragma unroll
-        for (int q = 0; q < TW; ++q) tp[(long)q * ldt] = (q == S) ? -1.f : 0.f;
+        for (int q = 0; q < S; ++q) tp[(long)q * ldt] = 0.f;
+        tp[(long)S * ldt] = r;  // NaN marks the masked step
       }
       const bool change = (phase == r_dur - 1);
       kf_predict<S>(ks, ql, qd, change);
@@ -109,7 +114,7 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
   }
   const float ll = -0.5f * (acc + (float)nobs * CI_LOG_2PI);
 
-  // ---- reverse: 8 adjoint steps + beta_bar accumulation per chunk ------------------------------
+  // ---- reverse: CI_TC adjoint steps + beta_bar accumulation per chunk --------------------------
   for (int j = 0; j < k; ++j) sb[j * sbld] = 0.f;
   KState<S> b;
 #pragma unroll
@@ -118,13 +123,13 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
   for (int i = 0; i < KState<S>::NP; ++i) b.P[i] = 0.f;
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
   phase = (T - 1) % r_dur;
-  for (int i = 7; i >= (T & 7) && (T & 7) != 0; --i) sr[(i >> 2) * srld + (i & 3)] = 0.f;
+  sr[0] = 0.f; sr[1] = 0.f; sr[2] = 0.f; sr[3] = 0.f;
   // software-pipelined tape reads: the entry of step t-1 is requested before step t is processed
   float cur[TW], nxt[TW] = {};
 #pragma unroll
   for (int q = 0; q < TW; ++q) cur[q] = tape[((long)(T - 1) * TW + q) * ldt];
   for (int t = T - 1; t >= 0; --t) {
-    const int i = t & 7;
+    const int i = t & (CI_TC - 1);
     if (t > 0) {
 #pragma unroll
       for (int q = 0; q < TW; ++q) nxt[q] = tape[((long)(t - 1) * TW + q) * ldt];
@@ -133,34 +138,52 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
     kb_predict_adj<S>(b, qlb, qdb, change);
     phase = (phase == 0) ? r_dur - 1 : phase - 1;
     float rb = 0.f;
-    if (cur[S] > 0.f) {
+    const float v = cur[S];
+    if (v == v) {
       float g[S];
 #pragma unroll
       for (int q = 0; q < S; ++q) g[q] = cur[q];
-      rb = kb_update_adj<S>(b, g, cur[S], cur[S + 1], Rb);
+      const float s = g[0] + (S > 1 ? g[1] : 0.f) + R;
+      rb = kb_update_adj<S>(b, g, s, v, Rb);
     }
-    sr[(i >> 2) * srld + (i & 3)] = rb;
-    if (i == 0 && k > 0) {
-      float rbv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) rbv[q] = sr[(q >> 2) * srld + (q & 3)];
-      const float* __restrict__ xp = Xn + (long)(t >> 3) * k * 8;
-#pragma unroll 4
-      for (int j = 0; j < k; ++j) {
-        const f4 x0 = load4(xp + j * 8), x1 = load4(xp + j * 8 + 4);
-        float a0 = sb[j * sbld], a1 = 0.f;
-        a0 = fmaf(-rbv[0], x0.x, a0); a1 = fmaf(-rbv[1], x0.y, a1);
-        a0 = fmaf(-rbv[2], x0.z, a0); a1 = fmaf(-rbv[3], x0.w, a1);
-        a0 = fmaf(-rbv[4], x1.x, a0); a1 = fmaf(-rbv[5], x1.y, a1);
-        a0 = fmaf(-rbv[6], x1.z, a0); a1 = fmaf(-rbv[7], x1.w, a1);
-        sb[j * sbld] = a0 + a1;
+    sr[i] = rb;
+    if (i == 0) {
+      const int tc = t / CI_TC;
+      if (tc != nchunk - 1) xs.acquire();       // the last forward chunk is still resident
+      if (k > 0) {
+        const float rb0 = sr[0], rb1 = sr[1], rb2 = sr[2], rb3 = sr[3];
+        const float* __restrict__ xp = xs.chunk(tc);
+#pragma unroll 5
+        for (int j = 0; j < k; ++j) {
+          const f4 x = xs.load(xp + j * CI_TC);
+          float a0 = sb[j * sbld], a1;
+          a0 = fmaf(-rb0, x.x, a0); a1 = -rb1 * x.y;
+          a0 = fmaf(-rb2, x.z, a0); a1 = fmaf(-rb3, x.w, a1);
+          sb[j * sbld] = a0 + a1;
+        }
       }
+      xs.release(tc - 1);                        // chunk tc-1 streams in during the next CI_TC steps
     }
 #pragma unroll
     for (int q = 0; q < TW; ++q) cur[q] = nxt[q];
   }
   params_backward_lane(u, ld, k, S, sc, scld, sb, sbld, Rb, qlb, qdb, grad);
   *logp_out = ll + ls.lp0;
+}
+
+// Barrier-only twin of eval_lane for the padding lanes of the last CTA: the same sequence of
+// acquire / release calls, no arithmetic and no stores.
+template <class XS>
+CI_HD void idle_lane(XS& xs, int T) {
+  const int nchunk = (T + CI_TC - 1) / CI_TC;
+  for (int tc = 0; tc < nchunk; ++tc) {
+    xs.acquire();
+    xs.release(tc + 1 < nchunk ? tc + 1 : -1);
+  }
+  for (int tc = nchunk - 1; tc >= 0; --tc) {
+    if (tc != nchunk - 1) xs.acquire();
+    xs.release(tc - 1);
+  }
 }
 
 }  // namespace ci

@@ -287,7 +287,7 @@ int ci_vi_fit(const ci_layout* L, const ci_data* D, int32_t units_per_series, in
               int32_t num_steps, float learning_rate, float init_scale, uint64_t seed, float* d_mu,
               float* d_rho, float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_layout(L)) return e;
-  CI_CHECK_ARG(D && D->d_y && D->d_sconst && (L->k == 0 || D->d_X), "NULL data pointer");
+  CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_mu && d_rho && d_workspace, "NULL pointer");
   CI_CHECK_ARG(units_per_series >= 1 && sample_size >= 1 && num_steps >= 0, "non-positive count");
   CI_CHECK_ARG(L->G == units_per_series * sample_size, "layout G must equal units_per_series * sample_size");
@@ -334,7 +334,7 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
                int32_t iter_offset, float* d_draws, float* d_stats, void* d_workspace, size_t workspace_bytes,
                void* stream) {
   if (int e = check_layout(L)) return e;
-  CI_CHECK_ARG(D && D->d_y && D->d_sconst && (L->k == 0 || D->d_X), "NULL data pointer");
+  CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_step0 && d_workspace, "NULL pointer");
   CI_CHECK_ARG(num_results >= 0 && num_warmup >= 0 && num_leapfrog >= 1, "bad iteration counts");
   CI_CHECK_ARG(num_adapt >= 0 && num_adapt <= num_warmup, "num_adapt must lie in [0, num_warmup]");

@@ -286,7 +286,7 @@ size_t ci_predict_workspace_bytes(const ci_layout* L) {
 int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, float* d_pred_mean,
                       float* d_pred_var, float* d_fstate, void* d_workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_layout(L)) return e;
-  CI_CHECK_ARG(D && D->d_y && D->d_sconst && (L->k == 0 || D->d_X), "NULL data pointer");
+  CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_pred_mean && d_pred_var && d_fstate && d_workspace, "NULL pointer");
   if (L->S > CI_MAX_REG_S) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < pred_ws_floats(L, nullptr, nullptr))
@@ -326,7 +326,7 @@ int ci_forecast_sample(const ci_layout* L, const ci_data* D, const float* d_u, c
                        const float* d_mu_sig, int32_t nsamp, uint64_t seed, float* d_post_sims,
                        float* d_post_mean, void* d_workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_layout(L)) return e;
-  CI_CHECK_ARG(D && D->d_y && D->d_sconst && (L->k == 0 || D->d_X), "NULL data pointer");
+  CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_fstate && d_workspace, "NULL pointer");
   CI_CHECK_ARG(L->Tf >= 1, "forecast horizon Tf must be >= 1");
   CI_CHECK_ARG(nsamp >= 0 && (nsamp == 0 || d_post_sims), "d_post_sims is NULL");

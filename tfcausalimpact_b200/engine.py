@@ -2,7 +2,7 @@
 
 Layout in HBM (float32, lane = fastest axis of every per-lane array):
     y      [N][T]          observed series (NaN = missing)
-    X      [N][Tpad/8][k][8] chunk-major design matrix (8 steps of a covariate = 32 contiguous bytes)
+    XY     [N][Tpad/4][k+1][4] chunk-major covariates + y (one TMA bulk copy per series-chunk)
     sconst [8][N]          per-series constants (mean, sd, m0, P0, prior hyper-parameters)
     u/grad [P][B]          unconstrained parameters / gradient, B = N * G lanes
 """
@@ -37,22 +37,20 @@ class DeviceBatch:
             assert X.shape[0] == self.N and X.shape[1] == self.T + self.Tf, \
                 f'design matrix must be [N, T+Tf, k], got {tuple(X.shape)}'
             self.k = X.shape[2]
-        self.Tpad = (self.T + self.Tf + 7) // 8 * 8
+        self.Tpad = (self.T + self.Tf + 3) // 4 * 4
         self.P = nt.num_params(self.k, self.S)
         self.sconst = torch.empty((8, self.N), dtype=torch.float32, device=self.device)
         L = self.layout(1)
         with torch.cuda.device(self.device):
             nt.check(self.lib.ci_series_stats(ctypes.byref(L), nt.ptr(self.y), ctypes.c_float(prior_level_sd),
                                               nt.ptr(self.sconst), nt.stream_ptr()), 'ci_series_stats')
-            if self.k > 0:
-                Xrm = X.to(self.device, torch.float32).contiguous()
-                self.X = torch.empty((self.N, self.Tpad // 8, self.k, 8), dtype=torch.float32, device=self.device)
-                nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.X), nt.stream_ptr()),
-                         'ci_pack_design')
+            Xrm = X.to(self.device, torch.float32).contiguous() if self.k > 0 else None
+            self.X = torch.empty((self.N, self.Tpad // 4, self.k + 1, 4), dtype=torch.float32, device=self.device)
+            nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.y), nt.ptr(self.X),
+                                             nt.stream_ptr()), 'ci_pack_design')
+            if Xrm is not None:
                 # stream-ordered: Xrm may be released once the pack kernel has been enqueued
                 Xrm.record_stream(torch.cuda.current_stream())
-            else:
-                self.X = None
         self._ws = {}
 
     # ------------------------------------------------------------------------------------------
@@ -60,7 +58,7 @@ class DeviceBatch:
         return nt.CiLayout(self.N, int(G), self.T, self.Tf, self.k, self.S, self.r, self.Tpad)
 
     def data(self):
-        return nt.CiData(nt.ptr(self.y).value, nt.ptr(self.X).value if self.X is not None else None,
+        return nt.CiData(nt.ptr(self.y).value, nt.ptr(self.X).value,
                          nt.ptr(self.sconst).value)
 
     def workspace(self, kind, nbytes):
@@ -225,7 +223,7 @@ class DeviceBatch:
 
 
 def _layout_for(N, T, Tf):
-    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 7) // 8 * 8)
+    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 3) // 4 * 4)
 
 
 def reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):

@@ -79,7 +79,7 @@ class CausalImpact:
             from .misc import maybe_unstandardize
             sims = maybe_unstandardize(np.squeeze(self.posterior_dist.sample(niter).numpy()), self.mu_sig)
         mask = np.asarray(self._mask, dtype=bool)
-        sims = sims[:, torch.as_tensor(mask, device=sims.device)] if torch.is_tensor(sims) else sims[:, mask]
+        sims = sims[:, torch.as_tensor(mask.copy(), device=sims.device)] if torch.is_tensor(sims) else sims[:, mask]
         post_masked = self.post_data[mask]
         self.summary_data = inferrer.summarize_posterior_inferences(
             self.inferences['post_preds_means'], post_masked, sims, self.alpha)
