@@ -14,7 +14,13 @@ template <int S>
 static void lane_eval(const float* u, long B, const float* sc, int N, const float* XYn, int T, int k, int r,
                       float* sb, float* sr, float* tape, float* logp, float* grad) {
   XDirect xs{XYn, (k + 1) * CI_TC};
-  eval_lane<S>(u, B, sc, N, xs, T, k, r, sb, 1, sr, tape, 1, logp, grad);
+  // same dispatch rule as launch_eval (ci_eval.cu)
+  if (r == 1 && S >= 2 && S <= CI_MAX_EFF_S) {
+    constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
+    eval_lane_eff<ES, 1>(u, B, sc, N, xs, T, k, sb, 1, sr, tape, ES + 1, logp, grad);
+  } else {
+    eval_lane<S>(u, B, sc, N, xs, T, k, r, sb, 1, sr, tape, 1, logp, grad);
+  }
 }
 
 // Runs ci::eval_lane -- the exact per-lane function the CUDA kernel k_eval executes -- for every lane.

@@ -56,10 +56,10 @@ struct Carver {
 
 // Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
-  float* tape;   // [T][S+1][B]  (g_0..g_{S-1}, v)
+  float* tape;   // [T][S+1][B] (g_0..g_{S-1}, v), or warp-blocked [T][B/32][S+1][32] (effects path)
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
-  const size_t B = (size_t)L->N * L->G;
+  const size_t B = ((size_t)L->N * L->G + 31) / 32 * 32;   // whole warps (warp-blocked tape layout)
   const size_t nt = (size_t)L->T * (L->S + 1) * B;
   if (ws && c) ws->tape = c->floats(nt);
   return align_up(nt * 4, 256);

@@ -84,7 +84,9 @@ __host__ __device__ inline int staged_series_max(int G) {
 // Registers are capped so that >= 640 lanes stay resident per SM for the small latent sizes
 // (S <= 7 -> <= 102 registers): 148 SMs x 640 = 94,720 lanes, i.e. the 80,000 lanes of the headline
 // workload run as ONE wave (the run time of a lane is fixed by its T sequential steps).
-template <int S, bool STAGED>
+// EFF selects the seasonal-effects formulation (ci_kalman_eff.cuh; season_duration == 1) with the
+// warp-blocked tape [T][warps][S+1][32] whose per-step addresses are one pointer bump + immediates.
+template <int S, bool STAGED, bool EFF>
 __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
        float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
@@ -119,14 +121,30 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
     }
     __syncthreads();
     if (threadIdx.x == 0) xs.issue(0);
-    if (valid)
-      eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
-    else
+    if (valid) {
+      if (EFF) {
+        constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
+        const long nwarp = (B + 31) / 32;
+        eval_lane_eff<ES, 32>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, EVAL_THREADS, sr,
+                              tape + (b >> 5) * ((ES + 1) * 32) + (b & 31), nwarp * ((ES + 1) * 32), logp + b, grad + b);
+      } else {
+        eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b,
+                     grad + b);
+      }
+    } else {
       idle_lane(xs, L.T);
+    }
   } else {
     if (!valid) return;
     XDirect xs{XY + (long)n * series_stride, stride};
-    eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+    if (EFF) {
+      constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
+      const long nwarp = (B + 31) / 32;
+      eval_lane_eff<ES, 32>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, EVAL_THREADS, sr,
+                            tape + (b >> 5) * ((ES + 1) * 32) + (b & 31), nwarp * ((ES + 1) * 32), logp + b, grad + b);
+    } else {
+      eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+    }
   }
 }
 
@@ -193,13 +211,13 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
   k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, beta, scal);
 }
 
-template <int S, bool STAGED>
+template <int S, bool STAGED, bool EFF>
 static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                          const EvalWs& ws, cudaStream_t st) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
   if (STAGED) smem += (size_t)staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 16;
-  auto kern = k_eval<S, STAGED>;
+  auto kern = k_eval<S, STAGED, EFF>;
   if (smem > 48 * 1024) {
     if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -217,10 +235,13 @@ static bool use_staging(const ci_layout* L) { return L->G >= 4 && L->k >= 4; }
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t st) {
   int rc = CI_OK;
+  const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   if (use_staging(L)) {
-    CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true>(L, D, d_u, d_logp, d_grad, ws, st)));
+    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false>(L, D, d_u, d_logp, d_grad, ws, st))); }
   } else {
-    CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false>(L, D, d_u, d_logp, d_grad, ws, st)));
+    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false>(L, D, d_u, d_logp, d_grad, ws, st))); }
   }
   if (rc) return rc;
   CI_CHECK_LAUNCH();

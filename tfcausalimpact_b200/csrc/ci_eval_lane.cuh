@@ -187,3 +187,184 @@ CI_HD void idle_lane(XS& xs, int T) {
 }
 
 }  // namespace ci
+
+// ================================================================================================
+// Seasonal-effects variant (ci_kalman_eff.cuh): season_duration == 1, 2 <= S <= CI_MAX_EFF_S.
+// Time is walked in blocks of S steps whose bodies are fully unrolled, so the season index of every
+// step is a compile-time constant and the state never moves between registers.
+//
+// Tape entry per step: g_0 .. g_{S-1}, v at tp[q * XS::TQ]  (g_S = -(g_1 + .. + g_{S-1}) because the
+// seasonal part of every covariance column sums to zero; s is recomputed; v = NaN = masked step).
+// Consecutive steps are `tstep` floats apart.
+// ================================================================================================
+#include "ci_kalman_eff.cuh"
+
+namespace ci {
+
+template <int S, class XS, int TQ>
+struct EffLane {
+  static constexpr int D = S + 1;
+  XS& xs;
+  const int T, k, nchunk, sbld;
+  float* __restrict__ sb;
+  float* __restrict__ sr;
+  float* tp;
+  const long tstep;
+  const float R, ql, q11, q1c, qcc, mean;
+  EState<S> st;
+  float acc = 0.f, comp = 0.f;
+  int nobs = 0;
+  float Rb = 0.f, qlb = 0.f, qdb = 0.f;
+  float cur[D], nxt[D];
+
+  CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, int sbld_, float* sr_, float* tape, long tstep_, float R_,
+                float ql_, float qd_, float mean_)
+      : xs(xs_), T(T_), k(k_), nchunk((T_ + CI_TC - 1) / CI_TC), sbld(sbld_), sb(sb_), sr(sr_), tp(tape),
+        tstep(tstep_), R(R_), ql(ql_), q11(qd_), q1c(-(float)(S - 1) * qd_), qcc((float)((S - 1) * (S - 1)) * qd_),
+        mean(mean_) {}
+
+  CI_HD void regress_fwd(int tc) {
+    xs.acquire();
+    const float* __restrict__ xp = xs.chunk(tc);
+    const f4 yv = xs.load(xp + k * CI_TC);
+    float r0 = yv.x - mean, r1 = yv.y - mean, r2 = yv.z - mean, r3 = yv.w - mean;
+#pragma unroll 2
+    for (int j = 0; j < k; ++j) {
+      const float bj = sb[j * sbld];
+      const f4 x = xs.load(xp + j * CI_TC);
+      r0 = fmaf(-bj, x.x, r0); r1 = fmaf(-bj, x.y, r1);
+      r2 = fmaf(-bj, x.z, r2); r3 = fmaf(-bj, x.w, r3);
+    }
+    sr[0] = r0; sr[1] = r1; sr[2] = r2; sr[3] = r3;
+    xs.release(tc + 1 < nchunk ? tc + 1 : -1);
+  }
+
+  CI_HD void regress_bwd(int tc) {
+    if (tc != nchunk - 1) xs.acquire();
+    if (k > 0) {
+      const float rb0 = sr[0], rb1 = sr[1], rb2 = sr[2], rb3 = sr[3];
+      const float* __restrict__ xp = xs.chunk(tc);
+#pragma unroll 2
+      for (int j = 0; j < k; ++j) {
+        const f4 x = xs.load(xp + j * CI_TC);
+        float a0 = sb[j * sbld], a1;
+        a0 = fmaf(-rb0, x.x, a0); a1 = -rb1 * x.y;
+        a0 = fmaf(-rb2, x.z, a0); a1 = fmaf(-rb3, x.w, a1);
+        sb[j * sbld] = a0 + a1;
+      }
+    }
+    xs.release(tc - 1);
+  }
+
+  template <int C>
+  CI_HD void fwd_step(int t) {
+    if (t >= T) return;
+    if ((t & (CI_TC - 1)) == 0) regress_fwd(t / CI_TC);
+    const float r = sr[t & (CI_TC - 1)];
+    if (r == r) {
+      float g[D], s, v, is;
+      ef_update<S, C>(st, r, R, g, s, v, is);
+#pragma unroll
+      for (int q = 0; q < S; ++q) tp[q * TQ] = g[q];
+      tp[S * TQ] = v;
+      const float term = logf(s) + v * v * is;
+      const float yk = term - comp;
+      const float tk = acc + yk;
+      comp = (tk - acc) - yk;
+      acc = tk;
+      ++nobs;
+    } else {
+#pragma unroll
+      for (int q = 0; q < S; ++q) tp[q * TQ] = 0.f;
+      tp[S * TQ] = r;
+    }
+    ef_predict<S, C>(st, ql, q11, q1c, qcc);
+    tp += tstep;
+  }
+
+  template <int C>
+  CI_HD void bwd_step(int t) {
+    if (t >= T) return;
+    // tp points at the entry of step t; request the entry of step t-1 before the arithmetic
+    if (t > 0) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) nxt[q] = (tp - tstep)[q * TQ];
+    }
+    eb_predict_adj<S, C>(st, qlb, qdb);
+    float rb = 0.f;
+    const float v = cur[S];
+    if (v == v) {
+      float g[D];
+      float gs = 0.f;
+#pragma unroll
+      for (int q = 0; q < S; ++q) {
+        g[q] = cur[q];
+        if (q >= 1) gs += cur[q];
+      }
+      g[S] = -gs;
+      const float s = g[0] + g[1 + C] + R;
+      rb = eb_update_adj<S, C>(st, g, s, v, Rb);
+    }
+    sr[t & (CI_TC - 1)] = rb;
+    if ((t & (CI_TC - 1)) == 0) regress_bwd(t / CI_TC);
+#pragma unroll
+    for (int q = 0; q < D; ++q) cur[q] = nxt[q];
+    tp -= tstep;
+  }
+};
+
+template <int S, class LaneT, int C>
+struct EffFwd {
+  static CI_HD void run(LaneT& L, int tb) {
+    L.template fwd_step<C>(tb + C);
+    EffFwd<S, LaneT, C + 1>::run(L, tb);
+  }
+};
+template <int S, class LaneT>
+struct EffFwd<S, LaneT, S> {
+  static CI_HD void run(LaneT&, int) {}
+};
+template <int S, class LaneT, int C>
+struct EffBwd {
+  static CI_HD void run(LaneT& L, int tb) {
+    L.template bwd_step<C>(tb + C);
+    EffBwd<S, LaneT, C - 1>::run(L, tb);
+  }
+};
+template <int S, class LaneT>
+struct EffBwd<S, LaneT, -1> {
+  static CI_HD void run(LaneT&, int) {}
+};
+
+// Same contract as eval_lane; `tape` is this lane's base pointer, entries TQ floats apart, steps
+// `tstep` floats apart (device: warp-blocked [T][warps][S+1][32], TQ = 32; host shim: TQ = 1).
+template <int S, int TQ, class XS>
+CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs,
+                         int T, int k, float* __restrict__ sb, int sbld, float* __restrict__ sr,
+                         float* __restrict__ tape, long tstep, float* __restrict__ logp_out,
+                         float* __restrict__ grad) {
+  const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, sbld);
+  using LaneT = EffLane<S, XS, TQ>;
+  LaneT L(xs, T, k, sb, sbld, sr, tape, tstep, ls.R, ls.ql, ls.qd, sc[SC_MEAN * scld]);
+  ef_init<S>(L.st, sc[SC_M0 * scld], sc[SC_P0 * scld]);
+  for (int tb = 0; tb < T; tb += S) EffFwd<S, LaneT, 0>::run(L, tb);
+  const float ll = -0.5f * (L.acc + (float)L.nobs * CI_LOG_2PI);
+
+  for (int j = 0; j < k; ++j) sb[j * sbld] = 0.f;
+#pragma unroll
+  for (int i = 0; i < S + 1; ++i) L.st.m[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < EState<S>::NP; ++i) L.st.P[i] = 0.f;
+  sr[0] = 0.f; sr[1] = 0.f; sr[2] = 0.f; sr[3] = 0.f;
+  L.tp -= tstep;  // entry of step T-1
+#pragma unroll
+  for (int q = 0; q < S + 1; ++q) {
+    L.cur[q] = L.tp[q * TQ];
+    L.nxt[q] = 0.f;
+  }
+  for (int tb = ((T - 1) / S) * S; tb >= 0; tb -= S) EffBwd<S, LaneT, S - 1>::run(L, tb);
+  params_backward_lane(u, ld, k, S, sc, scld, sb, sbld, L.Rb, L.qlb, L.qdb, grad);
+  *logp_out = ll + ls.lp0;
+}
+
+}  // namespace ci
