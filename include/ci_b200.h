@@ -51,7 +51,7 @@ typedef struct ci_layout {
 /* Caller-owned device inputs shared by every call on one batch of series. */
 typedef struct ci_data {
   const float* d_y;      /* [N][T]        observed series, NaN = missing step            */
-  const float* d_X;      /* [N][Tpad/4][k+1][4] chunk-major covariates + y (ci_pack_design) */
+  const float* d_X;      /* [Tpad/4][N][k+1][4] chunk-major covariates + y (ci_pack_design) */
   const float* d_sconst; /* [8][N]        per-series constants (see ci_series_stats)     */
 } ci_data;
 
@@ -68,8 +68,9 @@ int ci_num_params(int32_t k, int32_t S);
 int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, float* d_sconst,
                     void* stream);
 
-/* Row-major covariates [N][T+Tf][k] and the series [N][T] -> chunk-major [N][Tpad/4][k+1][4]:
- * 4 consecutive steps of one covariate are 16 contiguous bytes, row k of every chunk holds y
+/* Row-major covariates [N][T+Tf][k] and the series [N][T] -> chunk-major [Tpad/4][N][k+1][4]:
+ * 4 consecutive steps of one covariate are 16 contiguous bytes, the k+1 rows of a series follow each
+ * other and consecutive series are adjacent (one TMA bulk copy per warp and chunk); row k holds y
  * itself (NaN -> 0 in covariates, zero padded; NaN in y = missing).  Required for every layout,
  * also k = 0.  d_X_rowmajor may be NULL when k = 0.
  * Replaces: causalimpact/model.py:303-308 (concat(pre, post).astype(float32).fillna(0)). */

@@ -49,7 +49,7 @@ def synth_problem(N, T, Tf, k, S, r=1, seed=0, nan_frac=0.0, standardize=True):
 
 
 def pack_X(X, y, Tpad=None):
-    """X [N, Ttot, k], y [N, T] -> chunk-major XY [N, Tpad/4, k+1, 4] (row k = y, NaN past T)."""
+    """X [N, Ttot, k], y [N, T] -> chunk-major XY [Tpad/4, N, k+1, 4] (row k = y, NaN past T)."""
     N, Tt, k = X.shape
     T = y.shape[1]
     if Tpad is None:
@@ -58,7 +58,7 @@ def pack_X(X, y, Tpad=None):
     buf[:, :Tt, :k] = X
     buf[:, :, k] = np.nan
     buf[:, :T, k] = y
-    out = np.ascontiguousarray(buf.reshape(N, Tpad // 4, 4, k + 1).transpose(0, 1, 3, 2))
+    out = np.ascontiguousarray(buf.reshape(N, Tpad // 4, 4, k + 1).transpose(1, 0, 3, 2))
     return out, Tpad
 
 
@@ -118,10 +118,10 @@ def fptr(a):
 
 
 def shim_logp_grad(L, XY, Tpad, sconst, u_pb, G):
-    """XY: chunk-major [N, Tpad/4, k+1, 4]; u_pb: [P, B] float32 (lane fastest).
+    """XY: chunk-major [Tpad/4, N, k+1, 4]; u_pb: [P, B] float32 (lane fastest).
     Returns logp[B], grad[P, B]."""
     lib = host_shim()
-    N = XY.shape[0]
+    N = XY.shape[1]
     B = N * G
     logp = np.zeros(B, dtype=np.float32)
     grad = np.zeros((L.P, B), dtype=np.float32)

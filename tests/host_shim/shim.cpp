@@ -13,25 +13,25 @@ using namespace ci;
 template <int S>
 static void lane_eval(const float* u, long B, const float* sc, int N, const float* XYn, int T, int k, int r,
                       float* sb, float* sr, float* tape, float* logp, float* grad) {
-  XDirect xs{XYn, (k + 1) * CI_TC};
+  XDirect xs{XYn, (long)N * (k + 1) * CI_TC};
   // same dispatch rule as launch_eval (ci_eval.cu)
   if (r == 1 && S >= 2 && S <= CI_MAX_EFF_S) {
     constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
-    eval_lane_eff<ES, 1>(u, B, sc, N, xs, T, k, sb, 1, sr, tape, ES + 1, logp, grad);
+    eval_lane_eff<ES, 1, 1>(u, B, sc, N, xs, T, k, sb, sr, tape, ES + 1, logp, grad);
   } else {
     eval_lane<S>(u, B, sc, N, xs, T, k, r, sb, 1, sr, tape, 1, logp, grad);
   }
 }
 
 // Runs ci::eval_lane -- the exact per-lane function the CUDA kernel k_eval executes -- for every lane.
-// XY: chunk-major [N][Tpad/4][k+1][4] (row k = y).
+// XY: chunk-major [Tpad/4][N][k+1][4] (row k = y).
 extern "C" int shim_logp_grad(int N, int G, int T, int k, int S, int r, const float* XY, int Tpad,
                               const float* sconst, const float* u, float* logp, float* grad) {
   const long B = (long)N * G;
   std::vector<float> sb((size_t)(k > 0 ? k : 1)), sr(4), tape((size_t)T * (S + 1));
   for (long b = 0; b < B; ++b) {
     const int n = (int)(b / G);
-    CI_DISPATCH_S(S, (lane_eval<S_>(u + b, B, sconst + n, N, XY + (long)n * (k + 1) * Tpad, T, k, r, sb.data(),
+    CI_DISPATCH_S(S, (lane_eval<S_>(u + b, B, sconst + n, N, XY + (long)n * (k + 1) * CI_TC, T, k, r, sb.data(),
                                     sr.data(), tape.data(), logp + b, grad + b)));
   }
   return 0;

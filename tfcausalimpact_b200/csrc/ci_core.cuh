@@ -37,6 +37,44 @@ CI_HD float log_sigmoid(float u) {
   return (u < 0.f ? u : 0.f) - log1pf(expf(-fabsf(u)));
 }
 
+// Packed pair of floats: on sm_100a the pair arithmetic below compiles to the FP32x2 instructions
+// FFMA2 / FADD2 / FMUL2 (one issue slot for two IEEE-rounded operations, bit-identical to the scalar
+// forms); the host build (test shim) runs the same arithmetic as two scalar operations.
+#if defined(__CUDACC__)
+typedef float2 pf2;
+#else
+struct pf2 {
+  float x, y;
+};
+#endif
+CI_HD pf2 mk2(float a, float b) {
+  pf2 r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+CI_HD pf2 ffma2(pf2 a, pf2 b, pf2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+CI_HD pf2 fadd2(pf2 a, pf2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd2_rn(a, b);
+#else
+  return mk2(a.x + b.x, a.y + b.y);
+#endif
+}
+CI_HD pf2 fmul2(pf2 a, pf2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul2_rn(a, b);
+#else
+  return mk2(a.x * b.x, a.y * b.y);
+#endif
+}
+
 // Packed upper-triangular index of a symmetric SxS matrix (i <= j).
 template <int S>
 CI_HD constexpr int tri(int i, int j) {

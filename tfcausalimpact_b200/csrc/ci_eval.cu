@@ -28,28 +28,26 @@ constexpr int EVAL_THREADS = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// TMA-staged policy: the CTA's series share one staging buffer filled by cp.async.bulk.
+// TMA-staged policy: every WARP owns a staging buffer + mbarrier.  The series its 32 lanes belong to
+// are adjacent, so with the [chunk][series][k+1][4] layout the run it needs for one chunk is a single
+// contiguous block: ONE cp.async.bulk per (warp, chunk), issued by lane 0 as soon as the warp has
+// consumed the previous chunk (__syncwarp -- no CTA-wide barrier, warps never wait for each other).
 struct XStaged {
-  const float* lane_x;   // this lane's series slice of the staging buffer (shared memory)
-  uint32_t sx_addr;      // staging buffer base, shared-space address
-  uint32_t bar;          // mbarrier, shared-space address
+  const float* lane_x;   // this lane's series slice of the warp's staging buffer (shared memory)
+  uint32_t sx_addr;      // warp staging buffer, shared-space address
+  uint32_t bar;          // warp mbarrier, shared-space address
   uint32_t parity;
-  const float* gsrc;     // XY of the CTA's first series (global)
-  long series_stride;    // floats between consecutive series
-  int stride;            // floats per chunk = (k + 1) * CI_TC
-  int ns;                // series staged by this CTA
+  uint32_t bytes;        // bytes per (warp, chunk) = series_in_warp * (k + 1) * CI_TC * 4
+  const float* gsrc;     // XY[0][first series of the warp] (global)
+  long cstride;          // floats between consecutive chunks = N * (k + 1) * CI_TC
 
-  __device__ __forceinline__ void issue(int tc) const {   // one elected thread
-    const uint32_t bytes = (uint32_t)stride * 4u;
+  __device__ __forceinline__ void issue(int tc) const {   // lane 0 of the warp
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)ns)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sx_addr),
+                 "l"(gsrc + (long)tc * cstride), "r"(bytes), "r"(bar)
                  : "memory");
-    const float* src = gsrc + (long)tc * stride;
-    for (int s = 0; s < ns; ++s)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       sx_addr + (uint32_t)s * bytes),
-                   "l"(src + (long)s * series_stride), "r"(bytes), "r"(bar)
-                   : "memory");
   }
   __device__ __forceinline__ void acquire() {
     uint32_t ok;
@@ -63,10 +61,8 @@ struct XStaged {
     parity ^= 1u;
   }
   __device__ __forceinline__ void release(int next_tc) const {
-    // every lane of the CTA has consumed the staged chunk.  Non-.aligned barrier: the padding lanes
-    // of the last CTA arrive from idle_lane(), i.e. from a different program point of the same warp.
-    asm volatile("barrier.sync 0;" ::: "memory");
-    if (threadIdx.x == 0 && next_tc >= 0) issue(next_tc);
+    __syncwarp();   // every lane of the warp (padding lanes included) has consumed the staged chunk
+    if ((threadIdx.x & 31) == 0 && next_tc >= 0) issue(next_tc);
   }
   __device__ __forceinline__ const float* chunk(int) const { return lane_x; }
   __device__ __forceinline__ f4 load(const float* p) const {
@@ -75,10 +71,10 @@ struct XStaged {
   }
 };
 
-// Series one CTA of EVAL_THREADS lanes can touch (lanes of a series are contiguous).
+// Series one warp can touch (lanes of a series are contiguous).
 __host__ __device__ inline int staged_series_max(int G) {
-  const int a = (EVAL_THREADS + G - 2) / G + 1;
-  return a < EVAL_THREADS ? a : EVAL_THREADS;
+  const int a = (32 + G - 2) / G + 1;
+  return a < 32 ? a : 32;
 }
 
 // Registers are capped so that >= 640 lanes stay resident per SM for the small latent sizes
@@ -91,60 +87,61 @@ __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
        float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int NW = EVAL_THREADS / 32;
   const long B = (long)L.N * L.G;
-  const long b0 = (long)blockIdx.x * EVAL_THREADS;
-  const long b = b0 + threadIdx.x;
+  const long b = (long)blockIdx.x * EVAL_THREADS + threadIdx.x;
   const bool valid = b < B;
   const int n = (int)((valid ? b : B - 1) / L.G);
   const int stride = (L.k + 1) * CI_TC;
-  const long series_stride = (long)(L.Tpad / CI_TC) * stride;
+  const long cstride = (long)L.N * stride;
   float* sr = smem + threadIdx.x * 4;                     // [EVAL_THREADS][4]
   float* sb = smem + 4 * EVAL_THREADS + threadIdx.x;      // [k][EVAL_THREADS]
+  constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
+  const long nwarp = (B + 31) / 32;
+  float* tape_eff = tape + (b >> 5) * ((ES + 1) * 32) + (b & 31);
+  const long tstep_eff = nwarp * ((ES + 1) * 32);
   if (STAGED) {
-    float* sx = smem + (4 + L.k) * EVAL_THREADS;          // [ns][stride]
-    const int n_lo = (int)(b0 / L.G);
-    const long b_last = (b0 + EVAL_THREADS - 1 < B ? b0 + EVAL_THREADS - 1 : B - 1);
+    const int w = threadIdx.x >> 5;
+    const long bw0 = b - (threadIdx.x & 31);              // first lane of this warp
+    if (bw0 >= B) return;                                 // whole warp is padding: nothing to wait for
+    const int smax = staged_series_max(L.G);
+    float* sx = smem + (4 + L.k) * EVAL_THREADS + (long)w * smax * stride;   // [smax][stride] per warp
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (4 + L.k) * EVAL_THREADS + (long)NW * smax * stride) + w;
+    const int n_lo = (int)(bw0 / L.G);
+    const long b_last = (bw0 + 31 < B ? bw0 + 31 : B - 1);
     const int ns = (int)(b_last / L.G) - n_lo + 1;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sx + (long)staged_series_max(L.G) * stride);
     XStaged xs;
     xs.lane_x = sx + (long)(n - n_lo) * stride;
     xs.sx_addr = smem_u32(sx);
     xs.bar = smem_u32(bar);
     xs.parity = 0u;
-    xs.gsrc = XY + (long)n_lo * series_stride;
-    xs.series_stride = series_stride;
-    xs.stride = stride;
-    xs.ns = ns;
-    if (threadIdx.x == 0) {
+    xs.bytes = (uint32_t)ns * (uint32_t)stride * 4u;
+    xs.gsrc = XY + (long)n_lo * stride;
+    xs.cstride = cstride;
+    if ((threadIdx.x & 31) == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs.bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (threadIdx.x == 0) xs.issue(0);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) xs.issue(0);
     if (valid) {
-      if (EFF) {
-        constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
-        const long nwarp = (B + 31) / 32;
-        eval_lane_eff<ES, 32>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, EVAL_THREADS, sr,
-                              tape + (b >> 5) * ((ES + 1) * 32) + (b & 31), nwarp * ((ES + 1) * 32), logp + b, grad + b);
-      } else {
+      if (EFF)
+        eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
+                                            logp + b, grad + b);
+      else
         eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b,
                      grad + b);
-      }
     } else {
       idle_lane(xs, L.T);
     }
   } else {
     if (!valid) return;
-    XDirect xs{XY + (long)n * series_stride, stride};
-    if (EFF) {
-      constexpr int ES = (S >= 2 && S <= CI_MAX_EFF_S) ? S : 2;
-      const long nwarp = (B + 31) / 32;
-      eval_lane_eff<ES, 32>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, EVAL_THREADS, sr,
-                            tape + (b >> 5) * ((ES + 1) * 32) + (b & 31), nwarp * ((ES + 1) * 32), logp + b, grad + b);
-    } else {
+    XDirect xs{XY + (long)n * stride, cstride};
+    if (EFF)
+      eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
+                                          logp + b, grad + b);
+    else
       eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
-    }
   }
 }
 
@@ -180,7 +177,7 @@ __global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float*
 #pragma unroll
   for (int i = 0; i < CI_TC; ++i) a[i] = -mean;
   const int stride = (L.k + 1) * CI_TC;
-  XDirect xs{XY + (long)n * (L.Tpad / CI_TC) * stride, stride};
+  XDirect xs{XY + (long)n * stride, (long)L.N * stride};
   const float* __restrict__ xp = xs.chunk(tc);
   for (int j = 0; j < L.k; ++j) {
     const float bj = beta[(long)j * B + b];
@@ -216,7 +213,7 @@ static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u,
                          const EvalWs& ws, cudaStream_t st) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
-  if (STAGED) smem += (size_t)staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 16;
+  if (STAGED) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
   auto kern = k_eval<S, STAGED, EFF>;
   if (smem > 48 * 1024) {
     if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
@@ -295,7 +292,7 @@ __global__ void k_series_stats(int N, int T, int k, int S, double prior_level_sd
   sconst[SC_PRIOR_CONST * N + n] = (float)c;
 }
 
-// Row-major X [N][T+Tf][k] + y [N][T] -> chunk-major XY [N][Tpad/4][k+1][4]: rows 0..k-1 covariates
+// Row-major X [N][T+Tf][k] + y [N][T] -> chunk-major XY [Tpad/4][N][k+1][4]: rows 0..k-1 covariates
 // (NaN -> 0, zero padding past T+Tf), row k the observed series (NaN = missing / past T).
 __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const float* __restrict__ y,
                               float* __restrict__ XY) {
@@ -306,8 +303,8 @@ __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const 
   long rest = i / CI_TC;
   const int j = (int)(rest % (L.k + 1));
   rest /= (L.k + 1);
-  const int tc = (int)(rest % (L.Tpad / CI_TC));
-  const long n = rest / (L.Tpad / CI_TC);
+  const long n = rest % L.N;
+  const int tc = (int)(rest / L.N);
   const int t = tc * CI_TC + q;
   float v;
   if (j < L.k) {

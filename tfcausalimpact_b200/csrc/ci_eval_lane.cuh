@@ -7,10 +7,11 @@
 // beta_bar live in a per-lane scratch column (shared memory on the device), the CI_TC residuals of
 // the current time chunk in a second one, mean / covariance / adjoints in registers.
 //
-// Design matrix layout ("chunk-major"): XY[n][tc][j][CI_TC], tc = t / CI_TC, j = 0..k with row k
+// Design matrix layout ("chunk-major"): XY[tc][n][j][CI_TC], tc = t / CI_TC, j = 0..k with row k
 // holding the observed series y itself (NaN = missing) -- the k covariates and y of CI_TC consecutive
-// steps are one contiguous 16(k+1)-byte run, which the CUDA kernel stages into shared memory with one
-// TMA bulk copy per (series, chunk) while the previous chunk's filter steps run.
+// steps of one series are a contiguous 16(k+1)-byte run and consecutive series follow each other, so
+// the run a warp needs for a chunk (its 32/G series) is ONE contiguous block, which the CUDA kernel
+// stages into shared memory with one TMA bulk copy while the previous chunk's filter steps run.
 //
 // Tape entry per step: g_0..g_{S-1}, v  (s = g_0 + g_1 + R is recomputed; v = NaN marks a masked
 // step).
@@ -24,7 +25,8 @@
 #include "ci_kalman.cuh"
 #include "ci_params.cuh"
 
-#define CI_TC 4  // time steps per chunk
+#define CI_TC 4          // time steps per chunk
+#define CI_TAPE_AHEAD 4  // reverse sweep: L2 prefetch distance of the tape, in steps
 
 namespace ci {
 
@@ -32,13 +34,21 @@ struct f4 {
   float x, y, z, w;
 };
 
+CI_HD void prefetch_l2(const float* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // Direct policy: the lane reads its series' chunks straight from (global) memory.
 struct XDirect {
-  const float* base;  // XY[n]
-  int stride;         // floats per chunk = (k + 1) * CI_TC
+  const float* base;  // XY[0][n]
+  long cstride;       // floats between consecutive chunks of a series = N * (k + 1) * CI_TC
   CI_HD void acquire() {}
   CI_HD void release(int /*next_tc*/) {}
-  CI_HD const float* chunk(int tc) const { return base + (long)tc * stride; }
+  CI_HD const float* chunk(int tc) const { return base + (long)tc * cstride; }
   CI_HD f4 load(const float* p) const {
 #if defined(__CUDA_ARCH__)
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
@@ -201,12 +211,12 @@ CI_HD void idle_lane(XS& xs, int T) {
 
 namespace ci {
 
-template <int S, class XS, int TQ>
+template <int S, class XS, int TQ, int SBLD>
 struct EffLane {
   static constexpr int D = S + 1;
   XS& xs;
-  const int T, k, nchunk, sbld;
-  float* __restrict__ sb;
+  const int T, k, nchunk;
+  float* __restrict__ sb;   // beta_bar / MINUS beta column, element j at sb[j * SBLD]
   float* __restrict__ sr;
   float* tp;
   const long tstep;
@@ -217,50 +227,77 @@ struct EffLane {
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
   float cur[D], nxt[D];
 
-  CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, int sbld_, float* sr_, float* tape, long tstep_, float R_,
-                float ql_, float qd_, float mean_)
-      : xs(xs_), T(T_), k(k_), nchunk((T_ + CI_TC - 1) / CI_TC), sbld(sbld_), sb(sb_), sr(sr_), tp(tape),
-        tstep(tstep_), R(R_), ql(ql_), q11(qd_), q1c(-(float)(S - 1) * qd_), qcc((float)((S - 1) * (S - 1)) * qd_),
-        mean(mean_) {}
+  CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, float* sr_, float* tape, long tstep_, float R_, float ql_,
+                float qd_, float mean_)
+      : xs(xs_), T(T_), k(k_), nchunk((T_ + CI_TC - 1) / CI_TC), sb(sb_), sr(sr_), tp(tape), tstep(tstep_), R(R_),
+        ql(ql_), q11(qd_), q1c(-(float)(S - 1) * qd_), qcc((float)((S - 1) * (S - 1)) * qd_), mean(mean_) {}
 
+  // r_i = y_i - mean + sum_j (-beta_j) X_ji for the CI_TC steps of chunk tc (sb holds -beta).
   CI_HD void regress_fwd(int tc) {
     xs.acquire();
     const float* __restrict__ xp = xs.chunk(tc);
     const f4 yv = xs.load(xp + k * CI_TC);
-    float r0 = yv.x - mean, r1 = yv.y - mean, r2 = yv.z - mean, r3 = yv.w - mean;
-#pragma unroll 2
-    for (int j = 0; j < k; ++j) {
-      const float bj = sb[j * sbld];
-      const f4 x = xs.load(xp + j * CI_TC);
-      r0 = fmaf(-bj, x.x, r0); r1 = fmaf(-bj, x.y, r1);
-      r2 = fmaf(-bj, x.z, r2); r3 = fmaf(-bj, x.w, r3);
+    pf2 r01 = mk2(yv.x - mean, yv.y - mean), r23 = mk2(yv.z - mean, yv.w - mean);
+    const float* __restrict__ bp = sb;
+    int j = 0;
+    for (; j + 10 <= k; j += 10) {
+#pragma unroll
+      for (int q = 0; q < 10; ++q) {
+        const float nb = bp[q * SBLD];
+        const f4 x = xs.load(xp + q * CI_TC);
+        r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
+        r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
+      }
+      bp += 10 * SBLD;
+      xp += 10 * CI_TC;
     }
-    sr[0] = r0; sr[1] = r1; sr[2] = r2; sr[3] = r3;
+    for (; j < k; ++j) {
+      const float nb = bp[0];
+      const f4 x = xs.load(xp);
+      r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
+      r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
+      bp += SBLD;
+      xp += CI_TC;
+    }
+    sr[0] = r01.x; sr[1] = r01.y; sr[2] = r23.x; sr[3] = r23.y;
     xs.release(tc + 1 < nchunk ? tc + 1 : -1);
   }
 
+  // beta_bar_j -= sum_i rbar_i X_ji for the CI_TC steps of chunk tc.
   CI_HD void regress_bwd(int tc) {
     if (tc != nchunk - 1) xs.acquire();
     if (k > 0) {
-      const float rb0 = sr[0], rb1 = sr[1], rb2 = sr[2], rb3 = sr[3];
+      const pf2 n01 = mk2(-sr[0], -sr[1]), n23 = mk2(-sr[2], -sr[3]);
       const float* __restrict__ xp = xs.chunk(tc);
-#pragma unroll 2
-      for (int j = 0; j < k; ++j) {
-        const f4 x = xs.load(xp + j * CI_TC);
-        float a0 = sb[j * sbld], a1;
-        a0 = fmaf(-rb0, x.x, a0); a1 = -rb1 * x.y;
-        a0 = fmaf(-rb2, x.z, a0); a1 = fmaf(-rb3, x.w, a1);
-        sb[j * sbld] = a0 + a1;
+      float* __restrict__ bp = sb;
+      int j = 0;
+      for (; j + 10 <= k; j += 10) {
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const f4 x = xs.load(xp + q * CI_TC);
+          pf2 a = mk2(bp[q * SBLD], 0.f);
+          a = ffma2(mk2(x.x, x.y), n01, a);
+          a = ffma2(mk2(x.z, x.w), n23, a);
+          bp[q * SBLD] = a.x + a.y;
+        }
+        bp += 10 * SBLD;
+        xp += 10 * CI_TC;
+      }
+      for (; j < k; ++j) {
+        const f4 x = xs.load(xp);
+        pf2 a = mk2(bp[0], 0.f);
+        a = ffma2(mk2(x.x, x.y), n01, a);
+        a = ffma2(mk2(x.z, x.w), n23, a);
+        bp[0] = a.x + a.y;
+        bp += SBLD;
+        xp += CI_TC;
       }
     }
     xs.release(tc - 1);
   }
 
   template <int C>
-  CI_HD void fwd_step(int t) {
-    if (t >= T) return;
-    if ((t & (CI_TC - 1)) == 0) regress_fwd(t / CI_TC);
-    const float r = sr[t & (CI_TC - 1)];
+  CI_HD void fwd_step(float r) {
     if (r == r) {
       float g[D], s, v, is;
       ef_update<S, C>(st, r, R, g, s, v, is);
@@ -282,13 +319,16 @@ struct EffLane {
     tp += tstep;
   }
 
+  // tp points at the entry of the step being processed (already held in `cur`).
   template <int C>
-  CI_HD void bwd_step(int t) {
-    if (t >= T) return;
-    // tp points at the entry of step t; request the entry of step t-1 before the arithmetic
-    if (t > 0) {
+  CI_HD float bwd_step(bool more, bool far) {
+    if (more) {   // request the entry of the previous step before the arithmetic ...
 #pragma unroll
       for (int q = 0; q < D; ++q) nxt[q] = (tp - tstep)[q * TQ];
+    }
+    if (far) {    // ... and pull the entry CI_TAPE_AHEAD steps back from HBM into L2
+#pragma unroll
+      for (int q = 0; q < D; ++q) prefetch_l2((tp - CI_TAPE_AHEAD * tstep) + q * TQ);
     }
     eb_predict_adj<S, C>(st, qlb, qdb);
     float rb = 0.f;
@@ -305,52 +345,61 @@ struct EffLane {
       const float s = g[0] + g[1 + C] + R;
       rb = eb_update_adj<S, C>(st, g, s, v, Rb);
     }
-    sr[t & (CI_TC - 1)] = rb;
-    if ((t & (CI_TC - 1)) == 0) regress_bwd(t / CI_TC);
 #pragma unroll
     for (int q = 0; q < D; ++q) cur[q] = nxt[q];
     tp -= tstep;
+    return rb;
   }
-};
 
-template <int S, class LaneT, int C>
-struct EffFwd {
-  static CI_HD void run(LaneT& L, int tb) {
-    L.template fwd_step<C>(tb + C);
-    EffFwd<S, LaneT, C + 1>::run(L, tb);
+  // uniform dispatch on the (runtime) season index: every case has static register indices
+  template <int C>
+  CI_HD void disp_fwd(int c, float r) {
+    if (C == S - 1 || c == C) fwd_step<C>(r);
+    else disp_fwd<(C + 1 < S ? C + 1 : C)>(c, r);
   }
-};
-template <int S, class LaneT>
-struct EffFwd<S, LaneT, S> {
-  static CI_HD void run(LaneT&, int) {}
-};
-template <int S, class LaneT, int C>
-struct EffBwd {
-  static CI_HD void run(LaneT& L, int tb) {
-    L.template bwd_step<C>(tb + C);
-    EffBwd<S, LaneT, C - 1>::run(L, tb);
+  template <int C>
+  CI_HD float disp_bwd(int c, bool more, bool far) {
+    if (C == S - 1 || c == C) return bwd_step<C>(more, far);
+    else return disp_bwd<(C + 1 < S ? C + 1 : C)>(c, more, far);
   }
-};
-template <int S, class LaneT>
-struct EffBwd<S, LaneT, -1> {
-  static CI_HD void run(LaneT&, int) {}
+
+  CI_HD void forward() {
+    int c = 0;
+    for (int t = 0; t < T; ++t) {
+      const int i = t & (CI_TC - 1);
+      if (i == 0) regress_fwd(t / CI_TC);
+      disp_fwd<0>(c, sr[i]);
+      c = (c + 1 == S) ? 0 : c + 1;
+    }
+  }
+
+  CI_HD void backward() {
+    int c = (T - 1) % S;
+    for (int t = T - 1; t >= 0; --t) {
+      const int i = t & (CI_TC - 1);
+      sr[i] = disp_bwd<0>(c, t > 0, t >= CI_TAPE_AHEAD);
+      if (i == 0) regress_bwd(t / CI_TC);
+      c = (c == 0) ? S - 1 : c - 1;
+    }
+  }
 };
 
 // Same contract as eval_lane; `tape` is this lane's base pointer, entries TQ floats apart, steps
-// `tstep` floats apart (device: warp-blocked [T][warps][S+1][32], TQ = 32; host shim: TQ = 1).
-template <int S, int TQ, class XS>
+// `tstep` floats apart (device: warp-blocked [T][warps][S+1][32], TQ = 32; host shim: TQ = 1); the
+// scratch column stride SBLD is a compile-time constant so the regression loops address shared
+// memory with immediates.
+template <int S, int TQ, int SBLD, class XS>
 CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs,
-                         int T, int k, float* __restrict__ sb, int sbld, float* __restrict__ sr,
-                         float* __restrict__ tape, long tstep, float* __restrict__ logp_out,
-                         float* __restrict__ grad) {
-  const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, sbld);
-  using LaneT = EffLane<S, XS, TQ>;
-  LaneT L(xs, T, k, sb, sbld, sr, tape, tstep, ls.R, ls.ql, ls.qd, sc[SC_MEAN * scld]);
+                         int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
+                         long tstep, float* __restrict__ logp_out, float* __restrict__ grad) {
+  const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, SBLD, -1.0f);   // sb <- -beta
+  using LaneT = EffLane<S, XS, TQ, SBLD>;
+  LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd, sc[SC_MEAN * scld]);
   ef_init<S>(L.st, sc[SC_M0 * scld], sc[SC_P0 * scld]);
-  for (int tb = 0; tb < T; tb += S) EffFwd<S, LaneT, 0>::run(L, tb);
+  L.forward();
   const float ll = -0.5f * (L.acc + (float)L.nobs * CI_LOG_2PI);
 
-  for (int j = 0; j < k; ++j) sb[j * sbld] = 0.f;
+  for (int j = 0; j < k; ++j) sb[j * SBLD] = 0.f;
 #pragma unroll
   for (int i = 0; i < S + 1; ++i) L.st.m[i] = 0.f;
 #pragma unroll
@@ -362,8 +411,8 @@ CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __re
     L.cur[q] = L.tp[q * TQ];
     L.nxt[q] = 0.f;
   }
-  for (int tb = ((T - 1) / S) * S; tb >= 0; tb -= S) EffBwd<S, LaneT, S - 1>::run(L, tb);
-  params_backward_lane(u, ld, k, S, sc, scld, sb, sbld, L.Rb, L.qlb, L.qdb, grad);
+  L.backward();
+  params_backward_lane(u, ld, k, S, sc, scld, sb, SBLD, L.Rb, L.qlb, L.qdb, grad);
   *logp_out = ll + ls.lp0;
 }
 

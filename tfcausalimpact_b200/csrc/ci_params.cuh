@@ -40,7 +40,7 @@ struct LaneScalars {
 // u, beta: element stride `ld`.  sc: pointer to this series' constants with field stride `scld`.
 CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int k, int S,
                                       const float* __restrict__ sc, long scld, float* __restrict__ beta,
-                                      long ldb) {
+                                      long ldb, float beta_sign = 1.0f) {
   const float sd = sc[SC_SD * scld];
   LaneScalars o;
   const float u0 = u[0], u1 = u[ld];
@@ -56,15 +56,19 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
     const float ug = u[2 * ld], un = u[3 * ld];
     const float gsv = softplus(ug), gsn = softplus(un);
     lp += -1.5f * logf(gsv) - 0.5f / gsv - 0.5f * gsn * gsn + log_sigmoid(ug) + log_sigmoid(un);
-    const float G = gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE;
+    const float G = gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE * beta_sign;
     const float* ulsv = u + 4 * ld;
     const float* ulsn = u + (long)(4 + k) * ld;
     const float* uwn = u + (long)(4 + 2 * k) * ld;
+    // the loads of covariate j+1 are in flight while covariate j is processed
+    float a = ulsv[0], b = ulsn[0], wn = uwn[0];
     for (int j = 0; j < k; ++j) {
-      const float a = ulsv[(long)j * ld], b = ulsn[(long)j * ld], wn = uwn[(long)j * ld];
+      const int jn = (j + 1 < k) ? j + 1 : j;
+      const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
       const float lsv = softplus(a), lsn = softplus(b);
       lp += -1.5f * logf(lsv) - 0.5f / lsv - 0.5f * lsn * lsn - 0.5f * wn * wn + log_sigmoid(a) + log_sigmoid(b);
       beta[(long)j * ldb] = wn * lsn * sqrtf(lsv) * G;
+      a = an; b = bn; wn = wnn;
     }
   }
   if (S > 1) {
@@ -111,17 +115,20 @@ CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int
     float* glsn = grad + (long)(4 + k) * ld;
     float* gwn = grad + (long)(4 + 2 * k) * ld;
     float dG = 0.f;
+    float a = ulsv[0], b = ulsn[0], wn = uwn[0], bb = beta_bar[0];
     for (int j = 0; j < k; ++j) {
-      const float a = ulsv[(long)j * ld], b = ulsn[(long)j * ld], wn = uwn[(long)j * ld];
+      const int jn = (j + 1 < k) ? j + 1 : j;
+      const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
+      const float bbn = beta_bar[(long)jn * ldb];
       const float lsv = softplus(a), lsn = softplus(b);
       const float sq = sqrtf(lsv);
       const float l = lsn * sq;
-      const float bb = beta_bar[(long)j * ldb];
       dG = fmaf(bb, wn * l, dG);
       gwn[(long)j * ld] = bb * l * G - wn;
       const float dl = bb * wn * G;
       glsn[(long)j * ld] = (dl * sq - lsn) * sigmoid(b) + sigmoid(-b);
       glsv[(long)j * ld] = (dl * lsn * 0.5f / sq - 1.5f / lsv + 0.5f / (lsv * lsv)) * sigmoid(a) + sigmoid(-a);
+      a = an; b = bn; wn = wnn; bb = bbn;
     }
     grad[3 * ld] = (dG * sq_gsv * CI_WEIGHTS_PRIOR_SCALE - gsn) * sigmoid(un) + sigmoid(-un);
     grad[2 * ld] = (dG * gsn * CI_WEIGHTS_PRIOR_SCALE * 0.5f / sq_gsv - 1.5f / gsv + 0.5f / (gsv * gsv)) * sigmoid(ug) +

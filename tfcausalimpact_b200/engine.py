@@ -2,7 +2,7 @@
 
 Layout in HBM (float32, lane = fastest axis of every per-lane array):
     y      [N][T]          observed series (NaN = missing)
-    XY     [N][Tpad/4][k+1][4] chunk-major covariates + y (one TMA bulk copy per series-chunk)
+    XY     [Tpad/4][N][k+1][4] chunk-major covariates + y (one TMA bulk copy per warp and chunk)
     sconst [8][N]          per-series constants (mean, sd, m0, P0, prior hyper-parameters)
     u/grad [P][B]          unconstrained parameters / gradient, B = N * G lanes
 """
@@ -45,7 +45,7 @@ class DeviceBatch:
             nt.check(self.lib.ci_series_stats(ctypes.byref(L), nt.ptr(self.y), ctypes.c_float(prior_level_sd),
                                               nt.ptr(self.sconst), nt.stream_ptr()), 'ci_series_stats')
             Xrm = X.to(self.device, torch.float32).contiguous() if self.k > 0 else None
-            self.X = torch.empty((self.N, self.Tpad // 4, self.k + 1, 4), dtype=torch.float32, device=self.device)
+            self.X = torch.empty((self.Tpad // 4, self.N, self.k + 1, 4), dtype=torch.float32, device=self.device)
             nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.y), nt.ptr(self.X),
                                              nt.stream_ptr()), 'ci_pack_design')
             if Xrm is not None:
