@@ -70,12 +70,13 @@ int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, 
 
 /* Row-major covariates [N][T+Tf][k] and the series [N][T] -> chunk-major [Tpad/4][N][k+1][4]:
  * 4 consecutive steps of one covariate are 16 contiguous bytes, the k+1 rows of a series follow each
- * other and consecutive series are adjacent (one TMA bulk copy per warp and chunk); row k holds y
- * itself (NaN -> 0 in covariates, zero padded; NaN in y = missing).  Required for every layout,
+ * other and consecutive series are adjacent (one TMA bulk copy per warp and chunk); row k holds the
+ * centred series y - mean(y) (NaN -> 0 in covariates, zero padded; NaN in y = missing), so
+ * d_sconst must come from ci_series_stats on the same d_y.  Required for every layout,
  * also k = 0.  d_X_rowmajor may be NULL when k = 0.
  * Replaces: causalimpact/model.py:303-308 (concat(pre, post).astype(float32).fillna(0)). */
-int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d_y, float* d_XY_packed,
-                   void* stream);
+int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d_y, const float* d_sconst,
+                   float* d_XY_packed, void* stream);
 
 /* ---- K1-K3: joint log-prob + gradient in unconstrained space ------------------------------
  * Replaces: `model.joint_log_prob(observed_time_series)` + TF autodiff, causalimpact/model.py:375-377
@@ -164,6 +165,9 @@ int ci_reduce_inferences(const ci_layout* L, const float* d_y_pre, const float* 
 int ci_reduce_summary(const ci_layout* L, const float* d_y_post, const float* d_post_mean,
                       const float* d_post_sims, int32_t nsamp, float alpha, float* d_summary,
                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel launches one ci_kalman_logp_grad call enqueues (1: the evaluation is a single fused kernel). */
+int ci_eval_num_kernels(const ci_layout* L);
 
 /* FP32-FMA throughput probe used by bench.py as the measured CUDA-core roofline denominator
  * (MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only): `blocks` CTAs of 256 threads, 16

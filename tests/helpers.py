@@ -49,7 +49,7 @@ def synth_problem(N, T, Tf, k, S, r=1, seed=0, nan_frac=0.0, standardize=True):
 
 
 def pack_X(X, y, Tpad=None):
-    """X [N, Ttot, k], y [N, T] -> chunk-major XY [Tpad/4, N, k+1, 4] (row k = y, NaN past T)."""
+    """X [N, Ttot, k], y [N, T] -> chunk-major XY [Tpad/4, N, k+1, 4] (row k = y - mean(y), NaN past T)."""
     N, Tt, k = X.shape
     T = y.shape[1]
     if Tpad is None:
@@ -57,7 +57,7 @@ def pack_X(X, y, Tpad=None):
     buf = np.zeros((N, Tpad, k + 1), dtype=np.float32)
     buf[:, :Tt, :k] = X
     buf[:, :, k] = np.nan
-    buf[:, :T, k] = y
+    buf[:, :T, k] = y - np.nanmean(y.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
     out = np.ascontiguousarray(buf.reshape(N, Tpad // 4, 4, k + 1).transpose(1, 0, 3, 2))
     return out, Tpad
 

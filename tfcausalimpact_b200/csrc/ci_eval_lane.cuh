@@ -8,7 +8,7 @@
 // the current time chunk in a second one, mean / covariance / adjoints in registers.
 //
 // Design matrix layout ("chunk-major"): XY[tc][n][j][CI_TC], tc = t / CI_TC, j = 0..k with row k
-// holding the observed series y itself (NaN = missing) -- the k covariates and y of CI_TC consecutive
+// holding the centred observed series y - mean(y) (NaN = missing) -- the k covariates and y of CI_TC consecutive
 // steps of one series are a contiguous 16(k+1)-byte run and consecutive series follow each other, so
 // the run a warp needs for a chunk (its 32/G series) is ONE contiguous block, which the CUDA kernel
 // stages into shared memory with one TMA bulk copy while the previous chunk's filter steps run.
@@ -70,7 +70,6 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
   constexpr int TW = S + 1;
   const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, sbld);
   const float R = ls.R, ql = ls.ql, qd = ls.qd;
-  const float mean = sc[SC_MEAN * scld];
   const int nchunk = (T + CI_TC - 1) / CI_TC;
 
   // ---- forward: residual chunk (regression GEMV) + CI_TC filter steps --------------------------
@@ -86,7 +85,7 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
     {
       const float* __restrict__ xp = xs.chunk(tc);
       const f4 yv = xs.load(xp + k * CI_TC);
-      float r0 = yv.x - mean, r1 = yv.y - mean, r2 = yv.z - mean, r3 = yv.w - mean;
+      float r0 = yv.x, r1 = yv.y, r2 = yv.z, r3 = yv.w;   // row k holds the centred series
 #pragma unroll 5
       for (int j = 0; j < k; ++j) {
         const float bj = sb[j * sbld];
@@ -215,38 +214,53 @@ template <int S, class XS, int TQ, int SBLD>
 struct EffLane {
   static constexpr int D = S + 1;
   XS& xs;
-  const int T, k, nchunk;
+  const int T, k;
   float* __restrict__ sb;   // beta_bar / MINUS beta column, element j at sb[j * SBLD]
   float* __restrict__ sr;
   float* tp;
-  const long tstep;
-  const float R, ql, q11, q1c, qcc, mean;
+  const int tstep;
+  const float R, ql, q11;
   EState<S> st;
   float acc = 0.f, comp = 0.f;
   int nobs = 0;
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
   float cur[D], nxt[D];
 
-  CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, float* sr_, float* tape, long tstep_, float R_, float ql_,
-                float qd_, float mean_)
-      : xs(xs_), T(T_), k(k_), nchunk((T_ + CI_TC - 1) / CI_TC), sb(sb_), sr(sr_), tp(tape), tstep(tstep_), R(R_),
-        ql(ql_), q11(qd_), q1c(-(float)(S - 1) * qd_), qcc((float)((S - 1) * (S - 1)) * qd_), mean(mean_) {}
+  CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, float* sr_, float* tape, int tstep_, float R_, float ql_,
+                float qd_)
+      : xs(xs_), T(T_), k(k_), sb(sb_), sr(sr_), tp(tape), tstep(tstep_), R(R_), ql(ql_), q11(qd_) {}
+  CI_HD int nchunk() const { return (T + CI_TC - 1) / CI_TC; }
 
-  // r_i = y_i - mean + sum_j (-beta_j) X_ji for the CI_TC steps of chunk tc (sb holds -beta).
+  // r_i = (y_i - mean) + sum_j (-beta_j) X_ji for the CI_TC steps of chunk tc (sb holds -beta, row k
+  // of the chunk holds the centred series).  Loads are issued in batches of 5 covariates and the sums
+  // run in 4 independent FFMA2 chains so that shared-memory latency overlaps the arithmetic.
   CI_HD void regress_fwd(int tc) {
     xs.acquire();
     const float* __restrict__ xp = xs.chunk(tc);
     const f4 yv = xs.load(xp + k * CI_TC);
-    pf2 r01 = mk2(yv.x - mean, yv.y - mean), r23 = mk2(yv.z - mean, yv.w - mean);
+    pf2 r01 = mk2(yv.x, yv.y), r23 = mk2(yv.z, yv.w), s01 = mk2(0.f, 0.f), s23 = mk2(0.f, 0.f);
     const float* __restrict__ bp = sb;
     int j = 0;
     for (; j + 10 <= k; j += 10) {
 #pragma unroll
-      for (int q = 0; q < 10; ++q) {
-        const float nb = bp[q * SBLD];
-        const f4 x = xs.load(xp + q * CI_TC);
-        r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
-        r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
+      for (int h = 0; h < 10; h += 5) {
+        float nb[5];
+        f4 x[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          nb[q] = bp[(h + q) * SBLD];
+          x[q] = xs.load(xp + (h + q) * CI_TC);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          if ((h + q) & 1) {
+            s01 = ffma2(mk2(nb[q], nb[q]), mk2(x[q].x, x[q].y), s01);
+            s23 = ffma2(mk2(nb[q], nb[q]), mk2(x[q].z, x[q].w), s23);
+          } else {
+            r01 = ffma2(mk2(nb[q], nb[q]), mk2(x[q].x, x[q].y), r01);
+            r23 = ffma2(mk2(nb[q], nb[q]), mk2(x[q].z, x[q].w), r23);
+          }
+        }
       }
       bp += 10 * SBLD;
       xp += 10 * CI_TC;
@@ -259,13 +273,15 @@ struct EffLane {
       bp += SBLD;
       xp += CI_TC;
     }
+    r01 = fadd2(r01, s01);
+    r23 = fadd2(r23, s23);
     sr[0] = r01.x; sr[1] = r01.y; sr[2] = r23.x; sr[3] = r23.y;
-    xs.release(tc + 1 < nchunk ? tc + 1 : -1);
+    xs.release(tc + 1 < nchunk() ? tc + 1 : -1);
   }
 
   // beta_bar_j -= sum_i rbar_i X_ji for the CI_TC steps of chunk tc.
   CI_HD void regress_bwd(int tc) {
-    if (tc != nchunk - 1) xs.acquire();
+    if (tc != nchunk() - 1) xs.acquire();
     if (k > 0) {
       const pf2 n01 = mk2(-sr[0], -sr[1]), n23 = mk2(-sr[2], -sr[3]);
       const float* __restrict__ xp = xs.chunk(tc);
@@ -273,12 +289,20 @@ struct EffLane {
       int j = 0;
       for (; j + 10 <= k; j += 10) {
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
-          const f4 x = xs.load(xp + q * CI_TC);
-          pf2 a = mk2(bp[q * SBLD], 0.f);
-          a = ffma2(mk2(x.x, x.y), n01, a);
-          a = ffma2(mk2(x.z, x.w), n23, a);
-          bp[q * SBLD] = a.x + a.y;
+        for (int h = 0; h < 10; h += 5) {
+          f4 x[5];
+          pf2 a[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            x[q] = xs.load(xp + (h + q) * CI_TC);
+            a[q] = mk2(bp[(h + q) * SBLD], 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            a[q] = ffma2(mk2(x[q].x, x[q].y), n01, a[q]);
+            a[q] = ffma2(mk2(x[q].z, x[q].w), n23, a[q]);
+            bp[(h + q) * SBLD] = a[q].x + a[q].y;
+          }
         }
         bp += 10 * SBLD;
         xp += 10 * CI_TC;
@@ -315,7 +339,7 @@ struct EffLane {
       for (int q = 0; q < S; ++q) tp[q * TQ] = 0.f;
       tp[S * TQ] = r;
     }
-    ef_predict<S, C>(st, ql, q11, q1c, qcc);
+    ef_predict<S, C>(st, ql, q11, -(float)(S - 1) * q11, (float)((S - 1) * (S - 1)) * q11);
     tp += tstep;
   }
 
@@ -391,10 +415,10 @@ struct EffLane {
 template <int S, int TQ, int SBLD, class XS>
 CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs,
                          int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
-                         long tstep, float* __restrict__ logp_out, float* __restrict__ grad) {
+                         int tstep, float* __restrict__ logp_out, float* __restrict__ grad) {
   const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, SBLD, -1.0f);   // sb <- -beta
   using LaneT = EffLane<S, XS, TQ, SBLD>;
-  LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd, sc[SC_MEAN * scld]);
+  LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd);
   ef_init<S>(L.st, sc[SC_M0 * scld], sc[SC_P0 * scld]);
   L.forward();
   const float ll = -0.5f * (L.acc + (float)L.nobs * CI_LOG_2PI);

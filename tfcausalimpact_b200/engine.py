@@ -46,7 +46,7 @@ class DeviceBatch:
                                               nt.ptr(self.sconst), nt.stream_ptr()), 'ci_series_stats')
             Xrm = X.to(self.device, torch.float32).contiguous() if self.k > 0 else None
             self.X = torch.empty((self.Tpad // 4, self.N, self.k + 1, 4), dtype=torch.float32, device=self.device)
-            nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.y), nt.ptr(self.X),
+            nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.y), nt.ptr(self.sconst), nt.ptr(self.X),
                                              nt.stream_ptr()), 'ci_pack_design')
             if Xrm is not None:
                 # stream-ordered: Xrm may be released once the pack kernel has been enqueued
