@@ -65,9 +65,19 @@ inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   return align_up(nt * 4, 256);
 }
 
+// Optional leapfrog epilogue fused into the evaluation kernel (HMC): with the fresh gradient,
+//   p += (last ? 1/2 : 1) eps g ;  if (!last) u += eps p ,   eps = step0 * exp(logfac[lane]).
+struct LeapArgs {
+  float* pp = nullptr;            // [P][B] momentum (nullptr = no epilogue)
+  float* uu = nullptr;            // [P][B] position (the array being evaluated)
+  const float* step0 = nullptr;   // [P][B]
+  const float* logfac = nullptr;  // [B]
+  int last = 0;
+};
+
 // Enqueue one joint log-prob + gradient evaluation (one kernel) on `stream`.
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
-                const EvalWs& ws, cudaStream_t stream);
+                const EvalWs& ws, cudaStream_t stream, const LeapArgs* leap = nullptr);
 
 // out[t - t_lo][b] = with_y ? y_t - offset_t : offset_t, offset_t = mean + X_t . beta  (ci_eval.cu)
 void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, float* out, int t_lo, int t_hi,

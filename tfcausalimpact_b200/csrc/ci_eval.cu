@@ -82,10 +82,40 @@ __host__ __device__ inline int staged_series_max(int G) {
 // workload run as ONE wave (the run time of a lane is fixed by its T sequential steps).
 // EFF selects the seasonal-effects formulation (ci_kalman_eff.cuh; season_duration == 1) with the
 // warp-blocked tape [T][warps][S+1][32] whose per-step addresses are one pointer bump + immediates.
+__device__ __forceinline__ void leap_epilogue(const LeapArgs& lf, int P, long B, long b,
+                                              const float* __restrict__ grad) {
+  if (lf.pp == nullptr) return;
+  float* __restrict__ pp = lf.pp + b;
+  float* __restrict__ uu = lf.uu + b;
+  const float* __restrict__ st = lf.step0 + b;
+  const float* __restrict__ gr = grad + b;
+  const float fac = expf(lf.logfac[b]);
+  const float c = lf.last ? 0.5f : 1.0f;
+  constexpr int U = 8;   // 8 parameters per round: 32 independent loads in flight
+  for (int i0 = 0; i0 < P; i0 += U) {
+    float e[U], g[U], p[U], x[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const long o = (long)(i0 + q < P ? i0 + q : P - 1) * B;
+      e[q] = st[o]; g[q] = gr[o]; p[q] = pp[o]; x[q] = uu[o];
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      if (i0 + q < P) {
+        const long o = (long)(i0 + q) * B;
+        const float eps = e[q] * fac;
+        const float ph = fmaf(c * eps, g[q], p[q]);
+        pp[o] = ph;
+        if (!lf.last) uu[o] = fmaf(eps, ph, x[q]);
+      }
+    }
+  }
+}
+
 template <int S, bool STAGED, bool EFF>
 __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
-k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
-       float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
+k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
+       float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, LeapArgs lf) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NW = EVAL_THREADS / 32;
   const long B = (long)L.N * L.G;
@@ -131,6 +161,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
       else
         eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b,
                      grad + b);
+      leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);
     } else {
       idle_lane(xs, L.T);
     }
@@ -142,6 +173,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
                                           logp + b, grad + b);
     else
       eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+    leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);
   }
 }
 
@@ -210,7 +242,7 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
 
 template <int S, bool STAGED, bool EFF>
 static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
-                         const EvalWs& ws, cudaStream_t st) {
+                         const EvalWs& ws, cudaStream_t st, const LeapArgs& lf) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
   if (STAGED) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
@@ -221,7 +253,7 @@ static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u,
     if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
-                                                                                      d_logp, d_grad, ws.tape);
+                                                                                      d_logp, d_grad, ws.tape, lf);
   return CI_OK;
 }
 
@@ -230,15 +262,16 @@ static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u,
 static bool use_staging(const ci_layout* L) { return L->G >= 4 && L->k >= 4; }
 
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
-                const EvalWs& ws, cudaStream_t st) {
+                const EvalWs& ws, cudaStream_t st, const LeapArgs* leap) {
   int rc = CI_OK;
+  const LeapArgs lf = leap ? *leap : LeapArgs();
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   if (use_staging(L)) {
-    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false>(L, D, d_u, d_logp, d_grad, ws, st))); }
+    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
   } else {
-    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false>(L, D, d_u, d_logp, d_grad, ws, st))); }
+    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
   }
   if (rc) return rc;
   CI_CHECK_LAUNCH();

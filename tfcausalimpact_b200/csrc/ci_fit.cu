@@ -201,19 +201,6 @@ __global__ void k_hmc_begin(long B, int P, uint32_t it, uint64_t seed, const flo
   lane[HL_H0 * B + b] = -lane[HL_LP * B + b] + 0.5f * ke;
 }
 
-// Kick with the fresh gradient (full, or half on the last leapfrog) and, unless last, drift.
-__global__ void k_hmc_leap(long B, int P, int last, const float* __restrict__ step0,
-                           const float* __restrict__ gg, float* __restrict__ uu, float* __restrict__ pp,
-                           const float* __restrict__ lane) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * P) return;
-  const long b = i % B;
-  const float eps = step0[i] * expf(lane[HL_LOGFAC * B + b]);
-  const float ph = fmaf((last ? 0.5f : 1.0f) * eps, gg[i], pp[i]);
-  pp[i] = ph;
-  if (!last) uu[i] = fmaf(eps, ph, uu[i]);
-}
-
 // Metropolis accept, state selection, dual averaging, draw output.
 __global__ void k_hmc_end(long B, int P, uint32_t it_rng, int it, int num_warmup, int num_adapt,
                           float target_accept, uint64_t seed, float* __restrict__ u, float* __restrict__ g,
@@ -349,7 +336,7 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
   hmc_ws_floats(L, &ws, &c);
   const long B = (long)L->N * L->G;
   const int P = num_params(L->k, L->S);
-  const unsigned gl = nblk(B, 128), ge = nblk(B * P, 256);
+  const unsigned gl = nblk(B, 128);
   k_hmc_reset<<<gl, 128, 0, st>>>(B, ws.lane);
   // log-prob and gradient at the initial state (cached between transitions, as TFP does)
   if (int e = launch_eval(L, D, d_u, ws.lane + HL_LP * B, ws.g, ws.ev, st)) return e;
@@ -357,8 +344,14 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
     const uint32_t it_rng = (uint32_t)(iter_offset + it);
     k_hmc_begin<<<gl, 128, 0, st>>>(B, P, it_rng, seed, d_step0, d_u, ws.g, ws.uu, ws.pp, ws.lane);
     for (int l = 0; l < num_leapfrog; ++l) {
-      if (int e = launch_eval(L, D, ws.uu, ws.lane + HL_LPNEW * B, ws.gg, ws.ev, st)) return e;
-      k_hmc_leap<<<ge, 256, 0, st>>>(B, P, l == num_leapfrog - 1, d_step0, ws.gg, ws.uu, ws.pp, ws.lane);
+      // kick (and, unless last, drift) fused into the evaluation kernel's epilogue
+      LeapArgs lf;
+      lf.pp = ws.pp;
+      lf.uu = ws.uu;
+      lf.step0 = d_step0;
+      lf.logfac = ws.lane + HL_LOGFAC * B;
+      lf.last = (l == num_leapfrog - 1);
+      if (int e = launch_eval(L, D, ws.uu, ws.lane + HL_LPNEW * B, ws.gg, ws.ev, st, &lf)) return e;
     }
     float* draw = it >= num_warmup ? d_draws + (size_t)(it - num_warmup) * P * B : nullptr;
     k_hmc_end<<<gl, 128, 0, st>>>(B, P, it_rng, it, num_warmup, num_adapt, target_accept, seed, d_u, ws.g, ws.uu,
