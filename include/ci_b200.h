@@ -174,6 +174,9 @@ int ci_eval_num_kernels(const ci_layout* L);
  * independent FMA chains per thread, `iters` rounds; *flops_out = FLOPs the launch performs. */
 int ci_bench_fma(int32_t iters, int32_t blocks, float* d_out, void* stream, double* flops_out);
 
+/* Same probe with the Blackwell FP32x2 instruction (FFMA2): same FLOPs, half the instructions. */
+int ci_bench_fma2(int32_t iters, int32_t blocks, float* d_out, void* stream, double* flops_out);
+
 #ifdef __cplusplus
 }
 #endif

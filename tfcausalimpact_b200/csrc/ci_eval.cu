@@ -454,3 +454,29 @@ extern "C" int ci_eval_num_kernels(const ci_layout* L) {
   (void)L;
   return 1;
 }
+
+// ---- FP32x2 (FFMA2) throughput probe: same FLOPs as ci_bench_fma, half the instructions --------------
+namespace ci {
+__global__ void __launch_bounds__(256) k_fma2_probe(int iters, float seed, float* __restrict__ out) {
+  float2 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = make_float2(seed + (float)(threadIdx.x + i) * 1e-3f, seed + (float)i * 2e-3f);
+  const float2 m = make_float2(0.999f + seed * 1e-6f, 0.998f + seed * 1e-6f), c = make_float2(1e-3f, 2e-3f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+}  // namespace ci
+
+extern "C" int ci_bench_fma2(int32_t iters, int32_t blocks, float* d_out, void* stream, double* flops_out) {
+  CI_CHECK_ARG(iters > 0 && blocks > 0 && d_out, "bad arguments");
+  ci::k_fma2_probe<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, d_out);
+  if (flops_out) *flops_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+  CI_CHECK_LAUNCH();
+  return CI_OK;
+}
