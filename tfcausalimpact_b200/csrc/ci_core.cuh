@@ -37,6 +37,22 @@ CI_HD float log_sigmoid(float u) {
   return (u < 0.f ? u : 0.f) - log1pf(expf(-fabsf(u)));
 }
 
+// softplus(u), log_sigmoid(u), sigmoid(u), sigmoid(-u) from ONE exp / log1p / reciprocal.
+struct SoftplusPack {
+  float sp, lsig, sig, nsig;
+};
+CI_HD SoftplusPack softplus_pack(float u) {
+  const float e = expf(-fabsf(u));
+  const float l = log1pf(e);
+  const float s = rcp(1.0f + e);
+  SoftplusPack r;
+  r.sp = (u > 0.f ? u : 0.f) + l;
+  r.lsig = (u < 0.f ? u : 0.f) - l;
+  r.sig = u >= 0.f ? s : e * s;
+  r.nsig = u >= 0.f ? e * s : s;
+  return r;
+}
+
 // Packed pair of floats: on sm_100a the pair arithmetic below compiles to the FP32x2 instructions
 // FFMA2 / FADD2 / FMUL2 (one issue slot for two IEEE-rounded operations, bit-identical to the scalar
 // forms); the host build (test shim) runs the same arithmetic as two scalar operations.

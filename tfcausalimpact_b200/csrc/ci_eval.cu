@@ -24,7 +24,7 @@ char* last_error_buf() {
   return buf;
 }
 
-constexpr int EVAL_THREADS = 64;
+constexpr int EVAL_THREADS = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -113,7 +113,7 @@ __device__ __forceinline__ void leap_epilogue(const LeapArgs& lf, int P, long B,
 }
 
 template <int S, bool STAGED, bool EFF>
-__global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 10 : 4))
+__global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 20 : 8))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
        float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, LeapArgs lf) {
   extern __shared__ __align__(16) float smem[];

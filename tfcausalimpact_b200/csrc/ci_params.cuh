@@ -44,18 +44,20 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
   const float sd = sc[SC_SD * scld];
   LaneScalars o;
   const float u0 = u[0], u1 = u[ld];
-  const float so = sd * softplus(u0), sl = sd * softplus(u1);
+  const SoftplusPack p0 = softplus_pack(u0), p1 = softplus_pack(u1);
+  const float so = sd * p0.sp, sl = sd * p1.sp;
   const float so2 = so * so, sl2 = sl * sl;
   float lp = sc[SC_PRIOR_CONST * scld];
-  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(so) - sc[SC_OBS_B * scld] / so2 + log_sigmoid(u0);
-  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(sl) - sc[SC_LEVEL_B * scld] / sl2 + log_sigmoid(u1);
+  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(so) - sc[SC_OBS_B * scld] / so2 + p0.lsig;
+  lp += -(2.f * CI_PRIOR_A + 1.f) * logf(sl) - sc[SC_LEVEL_B * scld] / sl2 + p1.lsig;
   o.R = so2;
   o.ql = sl2;
   o.qd = 0.f;
   if (k > 0) {
     const float ug = u[2 * ld], un = u[3 * ld];
-    const float gsv = softplus(ug), gsn = softplus(un);
-    lp += -1.5f * logf(gsv) - 0.5f / gsv - 0.5f * gsn * gsn + log_sigmoid(ug) + log_sigmoid(un);
+    const SoftplusPack pg = softplus_pack(ug), pn = softplus_pack(un);
+    const float gsv = pg.sp, gsn = pn.sp;
+    lp += -1.5f * logf(gsv) - 0.5f / gsv - 0.5f * gsn * gsn + pg.lsig + pn.lsig;
     const float G = gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE * beta_sign;
     const float* ulsv = u + 4 * ld;
     const float* ulsn = u + (long)(4 + k) * ld;
@@ -65,18 +67,20 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
     for (int j = 0; j < k; ++j) {
       const int jn = (j + 1 < k) ? j + 1 : j;
       const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
-      const float lsv = softplus(a), lsn = softplus(b);
-      lp += -1.5f * logf(lsv) - 0.5f / lsv - 0.5f * lsn * lsn - 0.5f * wn * wn + log_sigmoid(a) + log_sigmoid(b);
+      const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(b);
+      const float lsv = pa.sp, lsn = pb.sp;
+      lp += -1.5f * logf(lsv) - 0.5f * rcp(lsv) - 0.5f * lsn * lsn - 0.5f * wn * wn + pa.lsig + pb.lsig;
       beta[(long)j * ldb] = wn * lsn * sqrtf(lsv) * G;
       a = an; b = bn; wn = wnn;
     }
   }
   if (S > 1) {
     const float ud = u[(long)(num_params(k, S) - 1) * ld];
-    const float sdr = sd * softplus(ud);
+    const SoftplusPack pd = softplus_pack(ud);
+    const float sdr = sd * pd.sp;
     const float lg = logf(sdr);
     const float z = (lg - sc[SC_DRIFT_MU * scld]) * (1.0f / 3.0f);
-    lp += -lg - 0.5f * z * z + log_sigmoid(ud);
+    lp += -lg - 0.5f * z * z + pd.lsig;
     const float q = sdr * (1.0f / S);
     o.qd = q * q;
   }
@@ -93,19 +97,22 @@ CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int
   const float sd = sc[SC_SD * scld];
   {
     const float u0 = u[0];
-    const float so = sd * softplus(u0);
+    const SoftplusPack p = softplus_pack(u0);
+    const float so = sd * p.sp;
     const float dth = -(2.f * CI_PRIOR_A + 1.f) / so + 2.f * sc[SC_OBS_B * scld] / (so * so * so) + 2.f * so * Rb;
-    grad[0] = dth * sd * sigmoid(u0) + sigmoid(-u0);
+    grad[0] = dth * sd * p.sig + p.nsig;
   }
   {
     const float u1 = u[ld];
-    const float sl = sd * softplus(u1);
+    const SoftplusPack p = softplus_pack(u1);
+    const float sl = sd * p.sp;
     const float dth = -(2.f * CI_PRIOR_A + 1.f) / sl + 2.f * sc[SC_LEVEL_B * scld] / (sl * sl * sl) + 2.f * sl * qlb;
-    grad[ld] = dth * sd * sigmoid(u1) + sigmoid(-u1);
+    grad[ld] = dth * sd * p.sig + p.nsig;
   }
   if (k > 0) {
     const float ug = u[2 * ld], un = u[3 * ld];
-    const float gsv = softplus(ug), gsn = softplus(un);
+    const SoftplusPack pg = softplus_pack(ug), pn = softplus_pack(un);
+    const float gsv = pg.sp, gsn = pn.sp;
     const float sq_gsv = sqrtf(gsv);
     const float G = gsn * sq_gsv * CI_WEIGHTS_PRIOR_SCALE;
     const float* ulsv = u + 4 * ld;
@@ -120,27 +127,31 @@ CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int
       const int jn = (j + 1 < k) ? j + 1 : j;
       const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
       const float bbn = beta_bar[(long)jn * ldb];
-      const float lsv = softplus(a), lsn = softplus(b);
+      const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(b);
+      const float lsv = pa.sp, lsn = pb.sp;
       const float sq = sqrtf(lsv);
+      const float ilsv = rcp(lsv);
       const float l = lsn * sq;
       dG = fmaf(bb, wn * l, dG);
       gwn[(long)j * ld] = bb * l * G - wn;
       const float dl = bb * wn * G;
-      glsn[(long)j * ld] = (dl * sq - lsn) * sigmoid(b) + sigmoid(-b);
-      glsv[(long)j * ld] = (dl * lsn * 0.5f / sq - 1.5f / lsv + 0.5f / (lsv * lsv)) * sigmoid(a) + sigmoid(-a);
+      glsn[(long)j * ld] = (dl * sq - lsn) * pb.sig + pb.nsig;
+      // d sqrt(v)/dv = sqrt(v) / (2 v);  d log IG(.5,.5)/dv = -1.5 / v + 0.5 / v^2
+      glsv[(long)j * ld] = (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig;
       a = an; b = bn; wn = wnn; bb = bbn;
     }
-    grad[3 * ld] = (dG * sq_gsv * CI_WEIGHTS_PRIOR_SCALE - gsn) * sigmoid(un) + sigmoid(-un);
-    grad[2 * ld] = (dG * gsn * CI_WEIGHTS_PRIOR_SCALE * 0.5f / sq_gsv - 1.5f / gsv + 0.5f / (gsv * gsv)) * sigmoid(ug) +
-                   sigmoid(-ug);
+    grad[3 * ld] = (dG * sq_gsv * CI_WEIGHTS_PRIOR_SCALE - gsn) * pn.sig + pn.nsig;
+    grad[2 * ld] = (dG * gsn * CI_WEIGHTS_PRIOR_SCALE * 0.5f / sq_gsv - 1.5f / gsv + 0.5f / (gsv * gsv)) * pg.sig +
+                   pg.nsig;
   }
   if (S > 1) {
     const long id = (long)(num_params(k, S) - 1) * ld;
     const float ud = u[id];
-    const float sdr = sd * softplus(ud);
+    const SoftplusPack pd = softplus_pack(ud);
+    const float sdr = sd * pd.sp;
     const float lg = logf(sdr);
     const float dth = -1.0f / sdr - (lg - sc[SC_DRIFT_MU * scld]) / (9.0f * sdr) + 2.f * sdr * qdb * (1.0f / (S * S));
-    grad[id] = dth * sd * sigmoid(ud) + sigmoid(-ud);
+    grad[id] = dth * sd * pd.sig + pd.nsig;
   }
 }
 
