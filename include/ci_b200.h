@@ -127,9 +127,12 @@ int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* 
  * Replaces: tfp.sts.one_step_predictive (model.py:414-418) and the forward_filter half of
  * tfp.sts.forecast (model.py:446-451).  L->G = posterior draws per series.
  *   d_pred_mean, d_pred_var [T][B]  out  one-step-ahead predictive mean / variance of y_t
- *   d_fstate [(S + S(S+1)/2 + S(S+1)/2)][B] out  predicted latent mean, packed covariance and its
- *                                                packed lower Cholesky factor at step T         */
+ *   d_fstate [ci_fstate_floats(L) * B] out  predicted latent mean, covariance and its lower Cholesky
+ *                                           factor at step T (opaque; input of ci_forecast_sample) */
 size_t ci_predict_workspace_bytes(const ci_layout* L);
+/* floats per lane of d_fstate (allocate ci_fstate_floats(L) * N * G floats); the internal layout
+ * depends on the kernel path and is only consumed by ci_forecast_sample */
+size_t ci_fstate_floats(const ci_layout* L);
 int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, float* d_pred_mean,
                       float* d_pred_var, float* d_fstate, void* d_workspace, size_t workspace_bytes,
                       void* stream);

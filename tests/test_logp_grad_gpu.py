@@ -19,6 +19,11 @@ CASES = [
     (2, 1, 1, 33, 0.0, 2, 2),
     (12, 2, 4, 100, 0.0, 2, 2),
     (3, 1, 0, 20, 0.0, 7, 5),
+    # nseasons outside the register-resident set -> warp-per-lane shared-memory path (ci_bigd.cu)
+    (8, 1, 2, 60, 0.0, 3, 2),
+    (9, 2, 0, 75, 0.1, 2, 3),
+    (10, 3, 40, 90, 0.05, 2, 2),
+    (52, 1, 3, 130, 0.0, 2, 2),   # configs[4] latent size
 ]
 
 

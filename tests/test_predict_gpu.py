@@ -139,3 +139,31 @@ def test_forecast_sampler_single_draw_covariance():
     assert abs(s.sum(axis=1).var() / var_sum - 1.0) < 0.08
     emp = np.cov(s.T)
     assert np.abs(emp - C).max() < 0.12 * np.abs(C).max()
+
+
+BIG = [(2, 3, 50, 9, 2, 8, 1, 0.0), (2, 2, 64, 11, 0, 9, 2, 0.1), (1, 3, 120, 60, 1, 52, 1, 0.0)]
+
+
+@pytest.mark.parametrize('N,G,T,Tf,k,S,r,nan_frac', BIG)
+def test_big_latent_path_filter_and_forecast(N, G, T, Tf, k, S, r, nan_frac):
+    """nseasons outside the register-resident set: warp-per-lane kernels (ci_bigd.cu)."""
+    L, prob, db = _setup(N, T, Tf, k, S, r, 31, nan_frac)
+    B = N * G
+    u = _draws(L, B, 7)
+    ud = torch.as_tensor(u).cuda()
+    pm, pv, fs = db.filter_predict(ud)
+    series = torch.arange(B) // G
+    mean_o, var_o, _, _, _, _ = O.one_step_predictive(prob, torch.as_tensor(u.T.astype(np.float64)), series)
+    np.testing.assert_allclose(pm.cpu().numpy().T, mean_o.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(pv.cpu().numpy().T, var_o.numpy(), rtol=1e-4)
+    nsamp = 4000
+    sims, mean = db.forecast_sample(ud, fs, nsamp, seed=5)
+    means_o, vars_o = O.forecast_moments(prob, torch.as_tensor(u.T.astype(np.float64)), series)
+    means_o = means_o.numpy().reshape(N, G, Tf)
+    vars_o = vars_o.numpy().reshape(N, G, Tf)
+    np.testing.assert_allclose(mean.cpu().numpy(), means_o.mean(axis=1), rtol=1e-4, atol=1e-4)
+    s = sims.cpu().numpy().astype(np.float64)
+    mix_mean = means_o.mean(axis=1)
+    mix_var = (vars_o + means_o ** 2).mean(axis=1) - mix_mean ** 2
+    assert np.all(np.abs(s.mean(axis=1) - mix_mean) < 5 * np.sqrt(mix_var / nsamp))
+    assert np.all(np.abs(s.var(axis=1) / mix_var - 1.0) < 0.25)

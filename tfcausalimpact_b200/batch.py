@@ -31,7 +31,7 @@ def standardize_batch(y_pre, y_post, X):
 
 def causal_impact_batch(y_pre, y_post, X=None, fit_method='vi', nseasons=1, season_duration=1,
                         prior_level_sd=0.01, standardize=True, niter=1000, alpha=0.05, chains=1,
-                        num_results=100, seed=0, device=None):
+                        num_results=100, num_warmup=50, predictive_draws=None, seed=0, device=None):
     """y_pre [N,T], y_post [N,Tf] (NaN = missing), X [N,T+Tf,k] or None -> dict with
     'summary' [N,10,2] (rows SUMMARY_ROWS; columns average, cumulative), 'p_value' [N] and the
     posterior draws in unconstrained space.  Under torchrun the series are sharded over ranks and
@@ -56,7 +56,9 @@ def causal_impact_batch(y_pre, y_post, X=None, fit_method='vi', nseasons=1, seas
         mu, rho = db.vi_fit(chains, 5, 150, 0.1, 0.01, seed)
         u0 = db.vi_draw(mu, rho, 1, seed + 1)
         step0 = torch.nn.functional.softplus(rho).contiguous()
-        draws, stats = db.hmc_run(u0, step0, num_results, 50, 40, 15, 0.75, seed + 2)   # [R, P, N*C]
+        draws, stats = db.hmc_run(u0, step0, num_results, num_warmup, int(0.8 * num_warmup), 15, 0.75, seed + 2)
+        if predictive_draws is not None and predictive_draws < draws.shape[0]:
+            draws = draws[-predictive_draws:]                                        # thin: last draws of every chain
         # lanes of the predictive path = series x (chains x draws)
         R, P, B = draws.shape
         u = draws.view(R, P, N, chains).permute(1, 2, 3, 0).reshape(P, N * chains * R).contiguous()

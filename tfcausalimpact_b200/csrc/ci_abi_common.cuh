@@ -54,13 +54,24 @@ struct Carver {
   }
 };
 
+// ---- large-latent (warp-per-lane) path, ci_bigd.cu ---------------------------------------------
+bool big_supported(const ci_layout* L);
+size_t big_tape_floats(const ci_layout* L);
+size_t big_fstate_floats(const ci_layout* L);   // per lane, lane-contiguous [B][D + 2 D^2]
+int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                    float* tape, cudaStream_t stream);
+int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, float* pm, float* pv, float* fs,
+                      cudaStream_t stream);
+void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
+                         const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t stream);
+
 // Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
   float* tape;   // [T][S+1][B] (g_0..g_{S-1}, v), or warp-blocked [T][B/32][S+1][32] (effects path)
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   const size_t B = ((size_t)L->N * L->G + 31) / 32 * 32;   // whole warps (warp-blocked tape layout)
-  const size_t nt = (size_t)L->T * (L->S + 1) * B;
+  const size_t nt = ci_reg_path(L->S) ? (size_t)L->T * (L->S + 1) * B : big_tape_floats(L);
   if (ws && c) ws->tape = c->floats(nt);
   return align_up(nt * 4, 256);
 }

@@ -1,0 +1,423 @@
+// Large-latent path: ONE WARP per (series, chain[, sample]) lane, used when nseasons is outside the
+// register-resident set (e.g. nseasons = 52, BASELINE.json configs[4]).  Same model, seasonal-effects
+// coordinates (ci_kalman_eff.cuh: x = [level | e_0..e_{S-1}], H_t = e_level + e_c, F = I,
+// Q_t = diag(ql, qd w w^T) on season changes), any season_duration, runtime S.
+//
+// The D x D covariance (D = S + 1) and its adjoint live in shared memory as full row-major matrices;
+// lane l of the warp owns columns l, l + 32, ... of every row, so row sweeps are conflict-free
+// (consecutive lanes -> consecutive banks) and the rank-1 update, the rank-1 drift term and the
+// symmetric matvec of the adjoint need no shuffles: the row scalar (g_i, w_i) is a shared-memory
+// broadcast and the column scalars sit in registers.  Per step: O(D^2 / 32) FMAs per thread.
+//
+//   k_eval_big    joint log-prob + gradient (forward filter, tape [B][T][D+1], reverse adjoint sweep,
+//                 warp-cooperative regression GEMV / beta_bar)          replaces: as ci_eval.cu
+//   k_filter_big  forward filter per posterior draw -> one-step predictive mean / variance,
+//                 predicted state + guarded Cholesky                    replaces: as ci_predict.cu K6
+//   k_forecast_mean_big / k_forecast_sample_big   forecast mean path and joint trajectories   (K7)
+// Forecast-state layout of this path: lane-contiguous [B][D + 2 D^2] = m, P (full), chol(P) (full).
+#include "ci_abi_common.cuh"
+#include "ci_eval_lane.cuh"
+
+namespace ci {
+
+constexpr int BIG_WARPS = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct BigCtx {
+  int D, S, r, T, k, N;
+  long B;
+};
+
+__device__ __forceinline__ int season_of(int t, int S, int r) { return (t / r) % S; }
+__device__ __forceinline__ bool season_change(int t, int S, int r) { return S > 1 && (t % r) == r - 1; }
+// drift-direction weight of state index i (0 = level) when season c was just observed
+__device__ __forceinline__ float drift_w(int i, int c, int S) { return i == 0 ? 0.f : (i == 1 + c ? (float)(1 - S) : 1.f); }
+
+__device__ void big_init(float* P, float* m, int D, int S, float m0, float p0, int lane) {
+  const float off = S > 1 ? -p0 / (float)S : 0.f;
+  for (int i = 0; i < D; ++i)
+    for (int j = lane; j < D; j += 32) {
+      float v = 0.f;
+      if (i == 0 || j == 0) v = (i == 0 && j == 0) ? p0 : 0.f;
+      else v = (i == j) ? p0 + off : off;
+      P[i * D + j] = v;
+    }
+  for (int j = lane; j < D; j += 32) m[j] = (j == 0) ? m0 : 0.f;
+  __syncwarp();
+}
+
+// residual of step t for the warp's lane: centred y minus the regression, summed across the warp
+__device__ __forceinline__ float big_resid(const float* __restrict__ XY, const ci_layout& L, int n, int t,
+                                           const float* beta, int lane) {
+  const int stride = (L.k + 1) * CI_TC;
+  const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
+  float acc = 0.f;
+  for (int j = lane; j < L.k; j += 32) acc = fmaf(beta[j], __ldg(xp + j * CI_TC), acc);
+  acc = warp_sum(acc);
+  return __ldg(xp + L.k * CI_TC) - acc;
+}
+
+// One filter step on the shared-memory state.  Returns false when the step is masked.
+// Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
+__device__ __forceinline__ bool big_step(float* P, float* m, float* g, int D, int S, int c, bool change, float resid,
+                                         float R, float ql, float qd, float& s, float& v, float& is, int lane) {
+  const int J = S > 1 ? 1 + c : 0;
+  const bool obs = (resid == resid);
+  for (int i = lane; i < D; i += 32) g[i] = P[i * D] + (S > 1 ? P[i * D + J] : 0.f);
+  __syncwarp();
+  s = g[0] + (S > 1 ? g[J] : 0.f) + R;
+  v = resid - m[0] - (S > 1 ? m[J] : 0.f);
+  is = 1.0f / s;
+  const float vis = v * is;
+  __syncwarp();
+  if (obs)
+    for (int j = lane; j < D; j += 32) m[j] = fmaf(g[j], vis, m[j]);
+  const float qq = change ? qd : 0.f;
+  for (int i = 0; i < D; ++i) {
+    const float nki = obs ? -g[i] * is : 0.f;
+    const float qi = qq * drift_w(i, c, S);
+    for (int j = lane; j < D; j += 32) {
+      float p = P[i * D + j];
+      p = fmaf(nki, g[j], p);
+      p = fmaf(qi, drift_w(j, c, S), p);
+      P[i * D + j] = p;
+    }
+  }
+  if (lane == 0) P[0] += ql;
+  __syncwarp();
+  return obs;
+}
+
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+           float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = L.S, D = S > 1 ? S + 1 : 1, k = L.k, T = L.T, r = L.r;
+  const long B = (long)L.N * L.G;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long b = (long)blockIdx.x * BIG_WARPS + w;
+  if (b >= B) return;
+  const int n = (int)(b / L.G);
+  const int per_warp = 2 * D * D + 4 * D + (k > 0 ? k : 1) + 8;
+  float* P = smem + (long)w * per_warp;
+  float* Pb = P + D * D;
+  float* m = Pb + D * D;
+  float* g = m + D;
+  float* mb = g + D;
+  float* gb = mb + D;
+  float* beta = gb + D;
+  float* scal = beta + (k > 0 ? k : 1);
+  if (lane == 0) {
+    const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+    scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0;
+  }
+  __syncwarp();
+  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3];
+  big_init(P, m, D, S, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], lane);
+  float* tp = tape + b * (long)T * (D + 1);
+  double acc = 0.0;
+  int nobs = 0;
+  for (int t = 0; t < T; ++t) {
+    const int c = S > 1 ? season_of(t, S, r) : 0;
+    const float resid = big_resid(XY, L, n, t, beta, lane);
+    float s, v, is;
+    const bool obs = big_step(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    // g was read before the sweep overwrote nothing it depends on: tape it now
+    for (int j = lane; j < D; j += 32) tp[(long)t * (D + 1) + j] = g[j];
+    if (lane == 0) tp[(long)t * (D + 1) + D] = obs ? v : __int_as_float(0x7fc00000);
+    if (obs) {
+      acc += (double)(logf(s) + v * v * is);
+      ++nobs;
+    }
+    __syncwarp();
+  }
+  const float ll = -0.5f * ((float)acc + (float)nobs * CI_LOG_2PI);
+
+  // ---- reverse sweep -----------------------------------------------------------------------------
+  for (int i = lane; i < D * D; i += 32) Pb[i] = 0.f;
+  for (int j = lane; j < D; j += 32) mb[j] = 0.f;
+  for (int j = lane; j < k; j += 32) beta[j] = 0.f;   // becomes beta_bar
+  __syncwarp();
+  float Rb = 0.f, qlb = 0.f, qdb = 0.f;
+  const int stride = (k + 1) * CI_TC;
+  for (int t = T - 1; t >= 0; --t) {
+    const int c = S > 1 ? season_of(t, S, r) : 0;
+    const int J = S > 1 ? 1 + c : 0;
+    // adjoint of the time update
+    qlb += Pb[0];
+    if (season_change(t, S, r)) {
+      float part = 0.f;
+      for (int i = 1; i < D; ++i) {
+        const float wi = drift_w(i, c, S);
+        float rowp = 0.f;
+        for (int j = lane; j < D; j += 32) rowp = fmaf(Pb[i * D + j], drift_w(j, c, S), rowp);
+        part = fmaf(wi, rowp, part);
+      }
+      qdb += warp_sum(part);
+    }
+    const float v = tp[(long)t * (D + 1) + D];
+    float rbar = 0.f;
+    if (v == v) {
+      for (int j = lane; j < D; j += 32) g[j] = tp[(long)t * (D + 1) + j];
+      __syncwarp();
+      const float s = g[0] + (S > 1 ? g[J] : 0.f) + R;
+      const float is = 1.0f / s;
+      // Pg_j = sum_i Pbar[i][j] g_i for the lane's columns (Pbar symmetric); a = mbar.g; gPg = g.Pg
+      float pa = 0.f, pg = 0.f;
+      for (int j = lane; j < D; j += 32) {
+        float col = 0.f;
+        for (int i = 0; i < D; ++i) col = fmaf(Pb[i * D + j], g[i], col);
+        gb[j] = col;   // holds Pg for now
+        pa = fmaf(mb[j], g[j], pa);
+        pg = fmaf(g[j], col, pg);
+      }
+      const float a = warp_sum(pa), gPg = warp_sum(pg);
+      const float vis = v * is;
+      const float vb = (a - v) * is;
+      const float sbar = (gPg - a * v) * is * is - 0.5f * (is - vis * vis);
+      Rb += sbar;
+      for (int j = lane; j < D; j += 32)
+        gb[j] = fmaf(mb[j], vis, fmaf(-2.f * is, gb[j], (j == 0 || (S > 1 && j == J)) ? sbar : 0.f));
+      __syncwarp();
+      // Pbar += sym(gb H^T): column/row 0, then column/row J (two phases: (0,J) is touched by both)
+      for (int j = lane; j < D; j += 32) {
+        const float h = 0.5f * gb[j];
+        Pb[j * D] += h;
+        Pb[j] += h;
+      }
+      __syncwarp();
+      if (S > 1) {
+        for (int j = lane; j < D; j += 32) {
+          const float h = 0.5f * gb[j];
+          Pb[j * D + J] += h;
+          Pb[J * D + j] += h;
+        }
+      }
+      if (lane == 0) {
+        mb[0] -= vb;
+        if (S > 1) mb[J] -= vb;
+      }
+      __syncwarp();
+      rbar = vb;
+      // beta_bar_j -= rbar X_tj
+      const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
+      for (int j = lane; j < k; j += 32) beta[j] = fmaf(-rbar, __ldg(xp + j * CI_TC), beta[j]);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
+    logp[b] = ll + lp0;
+  }
+}
+
+// Forward filter per draw lane: one-step predictive mean/variance + forecast state.
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+             float* __restrict__ pred_mean, float* __restrict__ pred_var, float* __restrict__ fstate) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = L.S, D = S > 1 ? S + 1 : 1, k = L.k, T = L.T, r = L.r;
+  const long B = (long)L.N * L.G;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long b = (long)blockIdx.x * BIG_WARPS + w;
+  if (b >= B) return;
+  const int n = (int)(b / L.G);
+  const int per_warp = 2 * D * D + 4 * D + (k > 0 ? k : 1) + 8;
+  float* P = smem + (long)w * per_warp;
+  float* Lc = P + D * D;
+  float* m = Lc + D * D;
+  float* g = m + D;
+  float* beta = g + 3 * D;
+  float* scal = beta + (k > 0 ? k : 1);
+  if (lane == 0) {
+    const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+    scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd;
+  }
+  __syncwarp();
+  const float R = scal[0], ql = scal[1], qd = scal[2];
+  const float mean = sconst[SC_MEAN * L.N + n];
+  big_init(P, m, D, S, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], lane);
+  for (int t = 0; t < T; ++t) {
+    const int c = S > 1 ? season_of(t, S, r) : 0;
+    const float resid = big_resid(XY, L, n, t, beta, lane);      // (y - mean) - X beta, NaN if masked
+    // offset_t = mean + X_t beta = y_t - resid when observed; recompute it for masked steps
+    const int stride = (k + 1) * CI_TC;
+    const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
+    float xb = 0.f;
+    for (int j = lane; j < k; j += 32) xb = fmaf(beta[j], __ldg(xp + j * CI_TC), xb);
+    xb = warp_sum(xb);
+    float s, v, is;
+    const float hm = m[0] + (S > 1 ? m[1 + c] : 0.f);
+    big_step(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    if (lane == 0) {
+      pred_mean[(long)t * B + b] = hm + mean + xb;
+      pred_var[(long)t * B + b] = s;
+    }
+  }
+  // forecast state: m, P, guarded Cholesky (relative pivot tolerance: P is singular along the
+  // zero-sum direction of the seasonal effects)
+  float* fs = fstate + b * (long)(D + 2 * D * D);
+  for (int j = lane; j < D; j += 32) fs[j] = m[j];
+  for (int i = lane; i < D * D; i += 32) {
+    fs[D + i] = P[i];
+    Lc[i] = 0.f;
+  }
+  float dmax = 0.f;
+  for (int i = 0; i < D; ++i) dmax = fmaxf(dmax, P[i * D + i]);
+  const float tol = 1e-6f * dmax;
+  __syncwarp();
+  for (int j = 0; j < D; ++j) {
+    // column j: d = P[j][j] - sum_q L[j][q]^2 ; L[i][j] = (P[i][j] - sum_q L[i][q] L[j][q]) / sqrt(d)
+    float part = 0.f;
+    for (int q = lane; q < j; q += 32) part = fmaf(Lc[j * D + q], Lc[j * D + q], part);
+    const float d = P[j * D + j] - warp_sum(part);
+    const float dj = d > tol ? sqrtf(d) : 0.f;
+    const float inv = dj > 0.f ? 1.0f / dj : 0.f;
+    for (int i = j + lane; i < D; i += 32) {
+      float a = P[i * D + j];
+      for (int q = 0; q < j; ++q) a = fmaf(-Lc[i * D + q], Lc[j * D + q], a);
+      Lc[i * D + j] = (i == j) ? dj : a * inv;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < D * D; i += 32) fs[D + D * D + i] = Lc[i];
+}
+
+__device__ __forceinline__ uint32_t pick_draw_big(uint32_t sample_id, uint32_t stream, int G, uint64_t seed) {
+  const float un = philox_uniform4(sample_id, 0u, stream, TAG_PICK, seed).x;
+  const int j = (int)(un * (float)G);
+  return (uint32_t)(j < G ? j : G - 1);
+}
+
+__global__ void k_forecast_mean_big(ci_layout L, const float* __restrict__ fstate, const float* __restrict__ off,
+                                    float* __restrict__ pm) {
+  const int S = L.S, D = S > 1 ? S + 1 : 1;
+  const long B = (long)L.N * L.G;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * L.Tf) return;
+  const long b = idx % B;
+  const int t = (int)(idx / B);
+  const float* fs = fstate + b * (long)(D + 2 * D * D);
+  const int c = S > 1 ? season_of(L.T + t, S, L.r) : 0;
+  pm[idx] = fs[0] + (S > 1 ? fs[1 + c] : 0.f) + off[idx];
+}
+
+#define CI_BIG_MAXD 96
+// One joint forecast trajectory per thread (state vector in local memory).
+__global__ void __launch_bounds__(128)
+k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __restrict__ fstate,
+                      const float* __restrict__ scal, const float* __restrict__ off,
+                      const float* __restrict__ mu_sig, float* __restrict__ sims) {
+  __shared__ float tile[128][33];
+  const int S = L.S, D = S > 1 ? S + 1 : 1, Tf = L.Tf, r = L.r;
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const long B = (long)L.N * L.G;
+  const long si = (long)n * nsamp + (i < nsamp ? i : 0);
+  const long b = (long)n * L.G + pick_draw_big((uint32_t)si, 1u, L.G, seed);
+  const float so = sqrtf(scal[0 * B + b]), sl = sqrtf(scal[1 * B + b]), sdr = sqrtf(scal[2 * B + b]);
+  const float mu = mu_sig ? mu_sig[n] : 0.f, sg = mu_sig ? mu_sig[L.N + n] : 1.f;
+  const float* fs = fstate + b * (long)(D + 2 * D * D);
+  const float* Lc = fs + D + D * D;
+  float x[CI_BIG_MAXD];
+  for (int a = 0; a < D; ++a) x[a] = fs[a];
+  for (int q = 0; q < (D + 3) / 4; ++q) {
+    const f32x4 zz = philox_normal4((uint32_t)si, (uint32_t)q, 0u, TAG_FORECAST_X0, seed);
+    const float z4[4] = {zz.x, zz.y, zz.z, zz.w};
+    for (int e = 0; e < 4; ++e) {
+      const int col = 4 * q + e;
+      if (col < D)
+        for (int a = col; a < D; ++a) x[a] = fmaf(Lc[a * D + col], z4[e], x[a]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t0 = 0; t0 < Tf; t0 += 32) {
+    const int tn = min(32, Tf - t0);
+    for (int q = 0; q < tn; ++q) {
+      const int t = t0 + q;
+      const int c = S > 1 ? season_of(L.T + t, S, r) : 0;
+      const f32x4 e = philox_normal4((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
+      const float yv = x[0] + (S > 1 ? x[1 + c] : 0.f) + off[(long)t * B + b] + so * e.x;
+      tile[threadIdx.x][q] = fmaf(yv, sg, mu);
+      x[0] = fmaf(sl, e.y, x[0]);
+      if (season_change(L.T + t, S, r)) {
+        const float xi = sdr * e.z;
+        for (int a = 1; a < D; ++a) x[a] += xi;
+        x[1 + c] -= (float)S * xi;    // net -(S-1) xi on the season just observed
+      }
+    }
+    __syncthreads();
+    for (int row = warp; row < 128; row += 4) {
+      const int ii = blockIdx.x * 128 + row;
+      if (ii < nsamp && lane < tn) sims[((long)n * nsamp + ii) * Tf + t0 + lane] = tile[row][lane];
+    }
+    __syncthreads();
+  }
+}
+
+size_t big_smem_bytes(const ci_layout* L) {
+  const int D = L->S > 1 ? L->S + 1 : 1;
+  return (size_t)BIG_WARPS * (2 * D * D + 4 * D + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
+}
+
+bool big_supported(const ci_layout* L) {
+  const int D = L->S > 1 ? L->S + 1 : 1;
+  return D <= CI_BIG_MAXD && big_smem_bytes(L) <= 227 * 1024;
+}
+
+size_t big_tape_floats(const ci_layout* L) {
+  const size_t D = L->S > 1 ? L->S + 1 : 1;
+  return (size_t)L->N * L->G * L->T * (D + 1);
+}
+
+size_t big_fstate_floats(const ci_layout* L) {
+  const size_t D = L->S > 1 ? L->S + 1 : 1;
+  return D + 2 * D * D;
+}
+
+template <class K>
+static int big_attr(K kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  return CI_OK;
+}
+
+int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                    float* tape, cudaStream_t st) {
+  if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  const size_t smem = big_smem_bytes(L);
+  if (int e = big_attr(k_eval_big, smem)) return e;
+  const long B = (long)L->N * L->G;
+  k_eval_big<<<(unsigned)((B + BIG_WARPS - 1) / BIG_WARPS), BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
+                                                                                      d_logp, d_grad, tape);
+  return CI_OK;
+}
+
+int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, float* pm, float* pv, float* fs,
+                      cudaStream_t st) {
+  if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  const size_t smem = big_smem_bytes(L);
+  if (int e = big_attr(k_filter_big, smem)) return e;
+  const long B = (long)L->N * L->G;
+  k_filter_big<<<(unsigned)((B + BIG_WARPS - 1) / BIG_WARPS), BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
+                                                                                        pm, pv, fs);
+  return CI_OK;
+}
+
+void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
+                         const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t st) {
+  const long B = (long)L->N * L->G;
+  const long tot = B * L->Tf;
+  k_forecast_mean_big<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*L, fs, off, pm);
+  if (sims)
+    k_forecast_sample_big<<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(*L, nsamp, seed, fs, scal, off, mu_sig, sims);
+}
+
+}  // namespace ci

@@ -1,5 +1,5 @@
 // Compile-time latent sizes served by the register-resident (thread-per-lane) kernels.
-// Larger nseasons go through the shared-memory CTA-per-lane path (ci_bigd.cu).
+// Every other nseasons goes through the shared-memory warp-per-lane path (ci_bigd.cu).
 #pragma once
 
 #define CI_MAX_REG_S 12
@@ -16,3 +16,6 @@
     case 12: { constexpr int S_ = 12; CALL; } break;   \
     default: return -3; /* CI_ERR_UNSUPPORTED */       \
   }
+
+// nseasons served by the register-resident kernels (must match the cases above)
+static inline bool ci_reg_path(int S) { return (S >= 1 && S <= 7) || S == 12; }

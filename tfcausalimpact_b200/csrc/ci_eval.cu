@@ -112,6 +112,11 @@ __device__ __forceinline__ void leap_epilogue(const LeapArgs& lf, int P, long B,
   }
 }
 
+__global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ grad) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) leap_epilogue(lf, P, B, b, grad);
+}
+
 template <int S, bool STAGED, bool EFF>
 __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 20 : 8))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
@@ -265,6 +270,15 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
                 const EvalWs& ws, cudaStream_t st, const LeapArgs* leap) {
   int rc = CI_OK;
   const LeapArgs lf = leap ? *leap : LeapArgs();
+  if (!ci_reg_path(L->S)) {   // large latent: warp-per-lane kernels + a separate leapfrog update
+    if (int e = launch_eval_big(L, D, d_u, d_logp, d_grad, ws.tape, st)) return e;
+    if (lf.pp) {
+      const long B = (long)L->N * L->G;
+      k_leap<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(lf, num_params(L->k, L->S), B, d_grad);
+    }
+    CI_CHECK_LAUNCH();
+    return CI_OK;
+  }
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   if (use_staging(L)) {
     if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
@@ -402,7 +416,8 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_logp && d_grad && d_workspace, "NULL pointer");
-  if (L->S > CI_MAX_REG_S) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
+  if (!ci_reg_path(L->S) && !big_supported(L))
+    return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_eval_workspace_bytes(L))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_eval_workspace_bytes(L));
   Carver c(d_workspace);

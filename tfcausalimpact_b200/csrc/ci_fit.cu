@@ -279,7 +279,8 @@ int ci_vi_fit(const ci_layout* L, const ci_data* D, int32_t units_per_series, in
   CI_CHECK_ARG(units_per_series >= 1 && sample_size >= 1 && num_steps >= 0, "non-positive count");
   CI_CHECK_ARG(L->G == units_per_series * sample_size, "layout G must equal units_per_series * sample_size");
   CI_CHECK_ARG(learning_rate > 0.f && init_scale > 0.f, "learning_rate and init_scale must be positive");
-  if (L->S > CI_MAX_REG_S) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
+  if (!ci_reg_path(L->S) && !big_supported(L))
+    return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_vi_workspace_bytes(L, units_per_series))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_vi_workspace_bytes(L, units_per_series));
   cudaStream_t st = (cudaStream_t)stream;
@@ -327,7 +328,8 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
   CI_CHECK_ARG(num_adapt >= 0 && num_adapt <= num_warmup, "num_adapt must lie in [0, num_warmup]");
   CI_CHECK_ARG(num_results == 0 || d_draws, "d_draws is NULL");
   CI_CHECK_ARG(target_accept > 0.f && target_accept < 1.f, "target_accept must lie in (0, 1)");
-  if (L->S > CI_MAX_REG_S) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
+  if (!ci_reg_path(L->S) && !big_supported(L))
+    return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_hmc_workspace_bytes(L))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_hmc_workspace_bytes(L));
   cudaStream_t st = (cudaStream_t)stream;

@@ -156,8 +156,7 @@ class DeviceBatch:
         """One-step-ahead predictive mean/variance [T,B] per draw + forecast prior state."""
         B = u.shape[1]
         L = self.layout(B // self.N)
-        S = self.S
-        nfs = S + S * (S + 1)
+        nfs = int(self.lib.ci_fstate_floats(ctypes.byref(L)))
         pm, pv, fs = self._f32(self.T, B), self._f32(self.T, B), self._f32(nfs, B)
         ws = self.workspace('pred', self.lib.ci_predict_workspace_bytes(ctypes.byref(L)))
         D = self.data()
