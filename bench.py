@@ -304,11 +304,19 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_eval_traffic.json')))
+        wl = tj['workload']
+        if (wl['series'], wl['chains'], wl['T'], wl['k'], wl['nseasons']) == (N, C, T, k, S):
+            traffic = tj['traffic_bytes_per_launch']      # dram read + write of one launch, ncu --set full
+    except Exception:
+        pass
     ach_tf = flops_per_eval / (eval_ms * 1e-3) / 1e12
     ach_gbs = bytes_per_eval / (eval_ms * 1e-3) / 1e9
     roofline = {
         'bound': 'fp32', 'kernel': 'ci_kalman_logp_grad (K1-K3 evaluation)', 'achieved': ach_tf,
-        'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / fp32_peak, 'traffic': None,
+        'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / fp32_peak, 'traffic': traffic,
         'peak_source': 'measured in this run (ci_bench_fma FFMA probe); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4',
         'frac_of_nominal': ach_tf / 74.4, 'ms_per_launch': eval_ms,
         'algorithmic_flops_per_launch': flops_per_eval, 'algorithmic_bytes_per_launch': bytes_per_eval,
