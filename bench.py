@@ -161,7 +161,7 @@ def cpu_step_time(args, ns, nsteps=1, seed=1):
 def cpu_calibrate(args):
     if args.cpu_sample_series > 0:
         return args.cpu_sample_series
-    ns = 8
+    ns = 32
     t = cpu_step_time(args, ns, 1)                   # dispatch-bound: cost grows slowly with lanes
     target = 12.0
     while ns < 128 and t * 1.7 < target:
