@@ -258,3 +258,31 @@ def reduce_summary(y_post, post_mean, post_sims, alpha):
                                        ctypes.c_int32(nsamp), ctypes.c_float(alpha), nt.ptr(out),
                                        ctypes.c_void_p(0), ctypes.c_size_t(0), nt.stream_ptr()), 'ci_reduce_summary')
     return out
+
+
+class HostUploader:
+    """Double-buffered host -> device staging on a side stream, so the PCIe copy of batch i+1
+    overlaps the kernels of batch i (pinned host tensors in, device tensors + ready event out)."""
+
+    def __init__(self, device):
+        nt.require_cuda()
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def start(self, *host_tensors):
+        """Enqueue the copies on the side stream; returns (device tensors, event)."""
+        with torch.cuda.stream(self.stream):
+            out = [None if t is None else t.to(self.device, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    @staticmethod
+    def finish(tensors, ev):
+        """Make the current stream wait for the copies and adopt the tensors."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(cur)
+        return tensors
