@@ -18,3 +18,25 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert lib.ci_version() >= 100
     assert lib.ci_num_params(50, 7) == 155 and lib.ci_num_params(0, 1) == 2 and lib.ci_num_params(1, 1) == 7
+
+
+def test_argument_validation_without_gpu():
+    """Invalid arguments are rejected before any CUDA call (error code + message, never a crash)."""
+    from tfcausalimpact_b200 import _native as nt
+    lib = nt.lib()
+    L = nt.make_layout(1, 1, 10, 2, 0, 1, 1)
+    bad = nt.CiLayout(0, 1, 10, 2, 0, 1, 1, 12)
+    assert lib.ci_eval_workspace_bytes(ctypes.byref(bad)) == 0
+    assert lib.ci_kalman_logp_grad(ctypes.byref(bad), None, None, None, None, None, ctypes.c_size_t(0), None) == -1
+    assert b'non-positive' in lib.ci_last_error_string()
+    assert lib.ci_kalman_logp_grad(ctypes.byref(L), None, None, None, None, None, ctypes.c_size_t(0), None) == -1
+    assert b'NULL' in lib.ci_last_error_string()
+    misaligned = nt.CiLayout(1, 1, 10, 2, 1, 1, 1, 13)
+    assert lib.ci_pack_design(ctypes.byref(misaligned), None, None, None, None, None) == -1
+    assert b'Tpad' in lib.ci_last_error_string()
+    r_without_s = nt.CiLayout(1, 1, 10, 2, 0, 1, 3, 12)
+    assert lib.ci_series_stats(ctypes.byref(r_without_s), None, ctypes.c_float(0.01), None, None) == -1
+    huge_s = nt.make_layout(1, 1, 10, 2, 0, 400, 1)
+    assert lib.ci_eval_workspace_bytes(ctypes.byref(huge_s)) > 0
+    assert lib.ci_fstate_floats(ctypes.byref(nt.make_layout(1, 1, 10, 2, 0, 7, 1))) == 7 + 7 * 8
+    assert lib.ci_fstate_floats(ctypes.byref(nt.make_layout(1, 1, 10, 2, 0, 52, 1))) == 53 + 2 * 53 * 53

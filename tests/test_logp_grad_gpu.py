@@ -19,6 +19,9 @@ CASES = [
     (2, 1, 1, 33, 0.0, 2, 2),
     (12, 2, 4, 100, 0.0, 2, 2),
     (3, 1, 0, 20, 0.0, 7, 5),
+    (7, 1, 5, 61, 0.05, 7, 6),     # staged path, series straddling warps (G = 6), ragged last chunk
+    (3, 1, 9, 41, 0.0, 11, 5),     # staged path, G = 5, partial last warp
+    (5, 2, 6, 50, 0.1, 4, 12),     # staged residual-basis path (season_duration 2)
     # nseasons outside the register-resident set -> warp-per-lane shared-memory path (ci_bigd.cu)
     (8, 1, 2, 60, 0.0, 3, 2),
     (9, 2, 0, 75, 0.1, 2, 3),
