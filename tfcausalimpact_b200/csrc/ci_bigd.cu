@@ -62,30 +62,62 @@ __device__ __forceinline__ float big_resid(const float* __restrict__ XY, const c
   return __ldg(xp + L.k * CI_TC) - acc;
 }
 
+// Column slots of a lane: columns lane, lane + 32, ... (NC = ceil(D / 32) of them, compile time so the
+// row sweeps are branch-uniform and the column scalars stay in registers).
+template <int NC>
+struct Cols {
+  int j[NC];
+  bool ok[NC];
+  __device__ __forceinline__ Cols(int lane, int D) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      j[q] = lane + 32 * q;
+      ok[q] = j[q] < D;
+      if (!ok[q]) j[q] = 0;   // harmless in-range address; never written
+    }
+  }
+};
+
 // One filter step on the shared-memory state.  Returns false when the step is masked.
 // Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
+template <int NC>
 __device__ __forceinline__ bool big_step(float* P, float* m, float* g, int D, int S, int c, bool change, float resid,
                                          float R, float ql, float qd, float& s, float& v, float& is, int lane) {
+  const Cols<NC> cl(lane, D);
   const int J = S > 1 ? 1 + c : 0;
   const bool obs = (resid == resid);
-  for (int i = lane; i < D; i += 32) g[i] = P[i * D] + (S > 1 ? P[i * D + J] : 0.f);
+  float gj[NC], wj[NC];
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    gj[q] = cl.ok[q] ? P[cl.j[q] * D] + (S > 1 ? P[cl.j[q] * D + J] : 0.f) : 0.f;
+    wj[q] = drift_w(cl.j[q], c, S);
+    if (cl.ok[q]) g[cl.j[q]] = gj[q];
+  }
   __syncwarp();
   s = g[0] + (S > 1 ? g[J] : 0.f) + R;
   v = resid - m[0] - (S > 1 ? m[J] : 0.f);
-  is = 1.0f / s;
+  is = rcp(s);
   const float vis = v * is;
   __syncwarp();
-  if (obs)
-    for (int j = lane; j < D; j += 32) m[j] = fmaf(g[j], vis, m[j]);
+  const float nis = obs ? -is : 0.f;
   const float qq = change ? qd : 0.f;
+  if (obs) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+      if (cl.ok[q]) m[cl.j[q]] = fmaf(gj[q], vis, m[cl.j[q]]);
+  }
+#pragma unroll 4
   for (int i = 0; i < D; ++i) {
-    const float nki = obs ? -g[i] * is : 0.f;
+    const float nki = g[i] * nis;
     const float qi = qq * drift_w(i, c, S);
-    for (int j = lane; j < D; j += 32) {
-      float p = P[i * D + j];
-      p = fmaf(nki, g[j], p);
-      p = fmaf(qi, drift_w(j, c, S), p);
-      P[i * D + j] = p;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      if (cl.ok[q]) {
+        float p = P[i * D + cl.j[q]];
+        p = fmaf(nki, gj[q], p);
+        p = fmaf(qi, wj[q], p);
+        P[i * D + cl.j[q]] = p;
+      }
     }
   }
   if (lane == 0) P[0] += ql;
@@ -93,6 +125,7 @@ __device__ __forceinline__ bool big_step(float* P, float* m, float* g, int D, in
   return obs;
 }
 
+template <int NC>
 __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
            float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
@@ -119,24 +152,31 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   __syncwarp();
   const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3];
   big_init(P, m, D, S, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], lane);
+  const Cols<NC> cl(lane, D);
   float* tp = tape + b * (long)T * (D + 1);
-  double acc = 0.0;
+  float acc = 0.f, comp = 0.f;
   int nobs = 0;
   for (int t = 0; t < T; ++t) {
     const int c = S > 1 ? season_of(t, S, r) : 0;
     const float resid = big_resid(XY, L, n, t, beta, lane);
     float s, v, is;
-    const bool obs = big_step(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
-    // g was read before the sweep overwrote nothing it depends on: tape it now
-    for (int j = lane; j < D; j += 32) tp[(long)t * (D + 1) + j] = g[j];
-    if (lane == 0) tp[(long)t * (D + 1) + D] = obs ? v : __int_as_float(0x7fc00000);
+    const bool obs = big_step<NC>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    float* te = tp + (long)t * (D + 1);
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+      if (cl.ok[q]) te[cl.j[q]] = g[cl.j[q]];
+    if (lane == 0) te[D] = obs ? v : __int_as_float(0x7fc00000);
     if (obs) {
-      acc += (double)(logf(s) + v * v * is);
+      const float term = logf(s) + v * v * is;
+      const float yk = term - comp;
+      const float tk = acc + yk;
+      comp = (tk - acc) - yk;
+      acc = tk;
       ++nobs;
     }
     __syncwarp();
   }
-  const float ll = -0.5f * ((float)acc + (float)nobs * CI_LOG_2PI);
+  const float ll = -0.5f * (acc + (float)nobs * CI_LOG_2PI);
 
   // ---- reverse sweep -----------------------------------------------------------------------------
   for (int i = lane; i < D * D; i += 32) Pb[i] = 0.f;
@@ -145,71 +185,118 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   __syncwarp();
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
   const int stride = (k + 1) * CI_TC;
+  // software-pipelined tape reads: the entry of step t-1 is requested before step t is processed
+  float cur_g[NC], cur_v, nxt_g[NC], nxt_v = 0.f;
+  {
+    const float* te = tp + (long)(T - 1) * (D + 1);
+    cur_v = te[D];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      cur_g[q] = cl.ok[q] ? te[cl.j[q]] : 0.f;
+      nxt_g[q] = 0.f;
+    }
+  }
   for (int t = T - 1; t >= 0; --t) {
     const int c = S > 1 ? season_of(t, S, r) : 0;
     const int J = S > 1 ? 1 + c : 0;
-    // adjoint of the time update
+    if (t > 0) {
+      const float* tn = tp + (long)(t - 1) * (D + 1);
+      nxt_v = tn[D];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) nxt_g[q] = cl.ok[q] ? tn[cl.j[q]] : 0.f;
+    }
+    const float v = cur_v;
+    const bool obs = (v == v);
+    const bool change = season_change(t, S, r);
+    float gj[NC], wj[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      gj[q] = obs ? cur_g[q] : 0.f;
+      wj[q] = cl.ok[q] ? drift_w(cl.j[q], c, S) : 0.f;
+      if (cl.ok[q]) g[cl.j[q]] = gj[q];
+    }
     qlb += Pb[0];
-    if (season_change(t, S, r)) {
-      float part = 0.f;
-      for (int i = 1; i < D; ++i) {
+    __syncwarp();
+    // one sweep over Pbar gives both the adjoint of the drift term (w^T Pbar w) and Pg = Pbar g
+    float col[NC], nac[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) col[q] = nac[q] = 0.f;
+    if (obs || change) {
+#pragma unroll 4
+      for (int i = 0; i < D; ++i) {
+        const float gi = g[i];
         const float wi = drift_w(i, c, S);
-        float rowp = 0.f;
-        for (int j = lane; j < D; j += 32) rowp = fmaf(Pb[i * D + j], drift_w(j, c, S), rowp);
-        part = fmaf(wi, rowp, part);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          const float pb = Pb[i * D + cl.j[q]];
+          col[q] = fmaf(pb, gi, col[q]);
+          nac[q] = fmaf(pb, wi, nac[q]);
+        }
       }
+    }
+    if (change) {
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) part = fmaf(wj[q], nac[q], part);
       qdb += warp_sum(part);
     }
-    const float v = tp[(long)t * (D + 1) + D];
-    float rbar = 0.f;
-    if (v == v) {
-      for (int j = lane; j < D; j += 32) g[j] = tp[(long)t * (D + 1) + j];
-      __syncwarp();
+    if (obs) {
       const float s = g[0] + (S > 1 ? g[J] : 0.f) + R;
-      const float is = 1.0f / s;
-      // Pg_j = sum_i Pbar[i][j] g_i for the lane's columns (Pbar symmetric); a = mbar.g; gPg = g.Pg
+      const float is = rcp(s);
       float pa = 0.f, pg = 0.f;
-      for (int j = lane; j < D; j += 32) {
-        float col = 0.f;
-        for (int i = 0; i < D; ++i) col = fmaf(Pb[i * D + j], g[i], col);
-        gb[j] = col;   // holds Pg for now
-        pa = fmaf(mb[j], g[j], pa);
-        pg = fmaf(g[j], col, pg);
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        if (cl.ok[q]) {
+          pa = fmaf(mb[cl.j[q]], gj[q], pa);
+          pg = fmaf(gj[q], col[q], pg);
+        }
       }
       const float a = warp_sum(pa), gPg = warp_sum(pg);
       const float vis = v * is;
       const float vb = (a - v) * is;
       const float sbar = (gPg - a * v) * is * is - 0.5f * (is - vis * vis);
       Rb += sbar;
-      for (int j = lane; j < D; j += 32)
-        gb[j] = fmaf(mb[j], vis, fmaf(-2.f * is, gb[j], (j == 0 || (S > 1 && j == J)) ? sbar : 0.f));
+      float gbj[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+        gbj[q] = cl.ok[q] ? fmaf(mb[cl.j[q]], vis,
+                                 fmaf(-2.f * is, col[q], (cl.j[q] == 0 || (S > 1 && cl.j[q] == J)) ? sbar : 0.f))
+                          : 0.f;
       __syncwarp();
       // Pbar += sym(gb H^T): column/row 0, then column/row J (two phases: (0,J) is touched by both)
-      for (int j = lane; j < D; j += 32) {
-        const float h = 0.5f * gb[j];
-        Pb[j * D] += h;
-        Pb[j] += h;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        if (cl.ok[q]) {
+          const float h = 0.5f * gbj[q];
+          Pb[cl.j[q] * D] += h;
+          Pb[cl.j[q]] += h;
+        }
       }
       __syncwarp();
       if (S > 1) {
-        for (int j = lane; j < D; j += 32) {
-          const float h = 0.5f * gb[j];
-          Pb[j * D + J] += h;
-          Pb[J * D + j] += h;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          if (cl.ok[q]) {
+            const float h = 0.5f * gbj[q];
+            Pb[cl.j[q] * D + J] += h;
+            Pb[J * D + cl.j[q]] += h;
+          }
         }
       }
       if (lane == 0) {
         mb[0] -= vb;
         if (S > 1) mb[J] -= vb;
       }
-      __syncwarp();
-      rbar = vb;
       // beta_bar_j -= rbar X_tj
       const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
-      for (int j = lane; j < k; j += 32) beta[j] = fmaf(-rbar, __ldg(xp + j * CI_TC), beta[j]);
+      for (int j = lane; j < k; j += 32) beta[j] = fmaf(-vb, __ldg(xp + j * CI_TC), beta[j]);
     }
+    cur_v = nxt_v;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) cur_g[q] = nxt_g[q];
     __syncwarp();
   }
+  (void)gb;
   if (lane == 0) {
     params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
     logp[b] = ll + lp0;
@@ -217,6 +304,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
 }
 
 // Forward filter per draw lane: one-step predictive mean/variance + forecast state.
+template <int NC>
 __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
              float* __restrict__ pred_mean, float* __restrict__ pred_var, float* __restrict__ fstate) {
@@ -253,7 +341,7 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
     xb = warp_sum(xb);
     float s, v, is;
     const float hm = m[0] + (S > 1 ? m[1 + c] : 0.f);
-    big_step(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    big_step<NC>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
     if (lane == 0) {
       pred_mean[(long)t * B + b] = hm + mean + xb;
       pred_var[(long)t * B + b] = s;
@@ -393,10 +481,16 @@ int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, floa
                     float* tape, cudaStream_t st) {
   if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
   const size_t smem = big_smem_bytes(L);
-  if (int e = big_attr(k_eval_big, smem)) return e;
   const long B = (long)L->N * L->G;
-  k_eval_big<<<(unsigned)((B + BIG_WARPS - 1) / BIG_WARPS), BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
-                                                                                      d_logp, d_grad, tape);
+  const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
+  const int Dl = L->S > 1 ? L->S + 1 : 1;
+#define CI_BIG_EVAL(NC)                                                                                    \
+  {                                                                                                        \
+    if (int e = big_attr(k_eval_big<NC>, smem)) return e;                                                  \
+    k_eval_big<NC><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape); \
+  }
+  if (Dl <= 32) CI_BIG_EVAL(1) else if (Dl <= 64) CI_BIG_EVAL(2) else CI_BIG_EVAL(3)
+#undef CI_BIG_EVAL
   return CI_OK;
 }
 
@@ -404,10 +498,16 @@ int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, fl
                       cudaStream_t st) {
   if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
   const size_t smem = big_smem_bytes(L);
-  if (int e = big_attr(k_filter_big, smem)) return e;
   const long B = (long)L->N * L->G;
-  k_filter_big<<<(unsigned)((B + BIG_WARPS - 1) / BIG_WARPS), BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
-                                                                                        pm, pv, fs);
+  const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
+  const int Dl = L->S > 1 ? L->S + 1 : 1;
+#define CI_BIG_FILTER(NC)                                                                              \
+  {                                                                                                    \
+    if (int e = big_attr(k_filter_big<NC>, smem)) return e;                                            \
+    k_filter_big<NC><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, pm, pv, fs);     \
+  }
+  if (Dl <= 32) CI_BIG_FILTER(1) else if (Dl <= 64) CI_BIG_FILTER(2) else CI_BIG_FILTER(3)
+#undef CI_BIG_FILTER
   return CI_OK;
 }
 
