@@ -57,3 +57,22 @@ def test_batch_agrees_with_single_series_api():
         hw_a = ci.summary_data.loc['predicted_upper', 'average'] - ci.summary_data.loc['predicted_lower', 'average']
         hw_b = summ[n, 3, 0] - summ[n, 2, 0]
         assert 0.6 < hw_a / hw_b < 1.6
+
+
+def test_causalimpact_batch_frontdoor():
+    from tfcausalimpact_b200 import CausalImpact
+    N, T, Tf, k = 8, 90, 21, 2
+    y_pre, y_post, X = _make(N, T, Tf, k, 7, 21, 2.5)
+    data = np.concatenate([np.concatenate([y_pre, y_post], axis=1)[:, :, None], X], axis=2)
+    res = CausalImpact.batch(data, [0, T - 1], [T, T + Tf - 1], model_args={'nseasons': 7, 'niter': 500}, seed=4)
+    assert len(res) == N
+    df = res.to_frame()
+    assert np.all(np.abs(df['abs_effect'].values - 2.5) < 0.8)
+    assert res.summary_data(0).shape == (10, 2)
+    assert res.summary(3).startswith('Posterior Inference {Causal Impact}')
+    with pytest.raises(ValueError) as e:
+        CausalImpact.batch(data, [0, T - 1], [T - 1, T + Tf - 1])
+    assert 'post_period first value' in str(e.value) or 'Values in training data' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        CausalImpact.batch(data, [0, T - 1], [T, T + Tf - 1], model_args={'fit_method': 'x'})
+    assert str(e.value) == 'fit_method can be either "hmc" or "vi".'

@@ -28,11 +28,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-struct BigCtx {
-  int D, S, r, T, k, N;
-  long B;
-};
-
 __device__ __forceinline__ int season_of(int t, int S, int r) { return (t / r) % S; }
 __device__ __forceinline__ bool season_change(int t, int S, int r) { return S > 1 && (t % r) == r - 1; }
 // drift-direction weight of state index i (0 = level) when season c was just observed

@@ -3,8 +3,10 @@
 //     F = blockdiag(1, A) on season-change steps (A z)_i = z_{i+1}, (A z)_{S-2} = -sum z,
 //     Q = blockdiag(ql, qd * 1 1^T) on season-change steps, diag(ql, 0) otherwise.
 // One *thread* owns one (series, chain[, sample]) lane: mean, packed-symmetric covariance and
-// their adjoints live in registers (S <= CI_MAX_REG_S); lanes are the fastest-moving index of
-// every global array so each warp access is one 128-byte line.
+// their adjoints live in registers (S <= CI_MAX_REG_S).  These are the step functions; the per-lane
+// drivers that chain them over time live in ci_eval_lane.cuh (fit) and ci_predict.cu (filter).
+// This residual-basis form serves season_duration > 1, nseasons = 1 and nseasons = 12; for
+// season_duration == 1 and 2 <= nseasons <= 7 the fit uses ci_kalman_eff.cuh.
 //
 // Replaces: tfd.LinearGaussianStateSpaceModel.log_prob + TF autodiff as reached from
 // /root/reference/causalimpact/model.py:361-364 (fit_with_hmc) and :374-381 (VI).
@@ -186,108 +188,6 @@ CI_HD float kb_update_adj(KState<S>& b, const float (&g)[S], float s, float v, f
   b.m[0] -= vb;
   if (S > 1) b.m[1] -= vb;
   return vb;
-}
-
-// ---- whole-lane driver -----------------------------------------------------------------------
-//
-// resid : [T] with element stride `ld`; in: r_t = y_t - offset_t (NaN = missing); out: dL/dr_t.
-// tape  : [T][S+2] with element stride `ld` (g_0..g_{S-1}, s (negative = masked), v).
-// Outputs: log-likelihood and adjoints of R = sigma_obs^2, ql = sigma_level^2, qd = (sigma_drift/S)^2.
-template <int S>
-CI_HD void kalman_logp_grad_lane(float* __restrict__ resid, float* __restrict__ tape, long ld, int T,
-                                 int r_dur, float R, float ql, float qd, float m0_level, float p0,
-                                 float& ll_out, float& Rb_out, float& qlb_out, float& qdb_out) {
-  constexpr int TW = S + 2;
-  KState<S> k;
-  kf_init<S>(k, m0_level, p0);
-  // log-likelihood accumulated as -0.5 * (sum log s + sum v^2/s) with a compensated sum
-  float acc = 0.f, comp = 0.f;
-  int nobs = 0;
-  int phase = 0;  // t mod r_dur
-  for (int t = 0; t < T; ++t) {
-    const float r = resid[(long)t * ld];
-    float* tp = tape + (long)t * TW * ld;
-    if (r == r) {
-      float g[S], s, v, is;
-      kf_update<S>(k, r, R, g, s, v, is);
-#pragma unroll
-      for (int i = 0; i < S; ++i) tp[(long)i * ld] = g[i];
-      tp[(long)S * ld] = s;
-      tp[(long)(S + 1) * ld] = v;
-      const float term = logf(s) + v * v * is;
-      const float yk = term - comp;
-      const float tk = acc + yk;
-      comp = (tk - acc) - yk;
-      acc = tk;
-      ++nobs;
-    } else {
-      tp[(long)S * ld] = -1.f;
-    }
-    const bool change = (phase == r_dur - 1);
-    kf_predict<S>(k, ql, qd, change);
-    phase = change ? 0 : phase + 1;
-  }
-  ll_out = -0.5f * (acc + (float)nobs * CI_LOG_2PI);
-
-  // reverse sweep
-  KState<S> b;
-#pragma unroll
-  for (int i = 0; i < S; ++i) b.m[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < KState<S>::NP; ++i) b.P[i] = 0.f;
-  float Rb = 0.f, qlb = 0.f, qdb = 0.f;
-  phase = (T - 1) % r_dur;
-  for (int t = T - 1; t >= 0; --t) {
-    const float* tp = tape + (long)t * TW * ld;
-    const bool change = (phase == r_dur - 1);
-    kb_predict_adj<S>(b, qlb, qdb, change);
-    phase = (phase == 0) ? r_dur - 1 : phase - 1;
-    const float s = tp[(long)S * ld];
-    float rb = 0.f;
-    if (s > 0.f) {
-      float g[S];
-#pragma unroll
-      for (int i = 0; i < S; ++i) g[i] = tp[(long)i * ld];
-      const float v = tp[(long)(S + 1) * ld];
-      rb = kb_update_adj<S>(b, g, s, v, Rb);
-    }
-    resid[(long)t * ld] = rb;
-  }
-  Rb_out = Rb;
-  qlb_out = qlb;
-  qdb_out = qdb;
-}
-
-// Forward-only filter used by the predictive path (one_step_predictive / forecast prior):
-// emits per-step predictive mean of the residual (H m) and variance s, and returns the predicted
-// state after the last step.  Masked steps still report (H m, s) from the prior, as TFP does.
-template <int S>
-CI_HD void kalman_filter_lane(const float* __restrict__ resid, long ld_in, float* __restrict__ hm_out,
-                              float* __restrict__ s_out, long ld_out, int T, int r_dur, float R, float ql,
-                              float qd, float m0_level, float p0, KState<S>& k) {
-  kf_init<S>(k, m0_level, p0);
-  int phase = 0;
-  for (int t = 0; t < T; ++t) {
-    const float r = resid[(long)t * ld_in];
-    if (r == r) {
-      float g[S], s, v, is;
-      kf_update<S>(k, r, R, g, s, v, is);
-      hm_out[(long)t * ld_out] = r - v;
-      s_out[(long)t * ld_out] = s;
-    } else {
-      float s = k.P[sym<S>(0, 0)] + R;
-      float hm = k.m[0];
-      if (S > 1) {
-        s += 2.f * k.P[sym<S>(0, 1)] + k.P[sym<S>(1, 1)];
-        hm += k.m[1];
-      }
-      hm_out[(long)t * ld_out] = hm;
-      s_out[(long)t * ld_out] = s;
-    }
-    const bool change = (phase == r_dur - 1);
-    kf_predict<S>(k, ql, qd, change);
-    phase = change ? 0 : phase + 1;
-  }
 }
 
 }  // namespace ci

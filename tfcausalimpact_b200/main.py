@@ -43,6 +43,49 @@ class CausalImpact:
         self._process_posterior_inferences()
         self._summarize_inferences()
 
+    @staticmethod
+    def batch(data, pre_period, post_period, model_args: Dict[str, Any] = {}, alpha: float = 0.05,
+              chains: int = 1, seed: int = 0):
+        """Many same-shaped series in ONE pass on the GPU (the reference can only
+        loop over `CausalImpact(...)` calls).
+
+        data: array [N, T_total, 1 + k] (column 0 = response, the rest covariates; NaN in the response
+        marks missing steps); pre_period / post_period: integer [first, last] positions, inclusive,
+        shared by all series; model_args / alpha as for the constructor (same validation and errors).
+        Returns a `BatchResult`."""
+        from .batch import causal_impact_batch
+        arr = np.asarray(data, dtype=np.float32)
+        if arr.ndim != 3 or arr.shape[0] < 1:
+            raise ValueError('data must be an array of shape [N, T, 1 + k].')
+        alpha = cidata.process_alpha(alpha)
+        args = cimodel.process_model_args(dict(model_args) if model_args else {})
+        frame = pd.DataFrame(arr[0])
+        pre, post = cidata.process_period(pre_period, frame), cidata.process_period(post_period, frame)
+        if pre[1] > post[0]:
+            raise ValueError('Values in training data cannot be present in the post-intervention '
+                             'data. Please fix your pre_period value to cover at most one point less '
+                             'from when the intervention happened.')
+        if pre[1] - pre[0] < 3:
+            raise ValueError('pre_period must span at least 3 time points.')
+        if post[1] < post[0]:
+            raise ValueError('post_period last number must be bigger than its first.')
+        if post[0] <= pre[1]:
+            raise ValueError(f'post_period first value ({post_period[0]}) must '
+                             'be bigger than the second value of pre_period '
+                             f'({pre_period[1]}).')
+        if arr.shape[2] > 1 and np.isnan(arr[:, :, 1:]).any():
+            raise ValueError('Input data cannot have NAN values.')
+        y_pre, y_post = arr[:, pre[0]:pre[1] + 1, 0], arr[:, post[0]:post[1] + 1, 0]
+        X = None
+        if arr.shape[2] > 1:
+            X = np.concatenate([arr[:, pre[0]:pre[1] + 1, 1:], arr[:, post[0]:post[1] + 1, 1:]], axis=1)
+        res = causal_impact_batch(np.ascontiguousarray(y_pre), np.ascontiguousarray(y_post), X,
+                                  fit_method=args['fit_method'], nseasons=args['nseasons'],
+                                  season_duration=args['season_duration'], prior_level_sd=args['prior_level_sd'],
+                                  standardize=args['standardize'], niter=args['niter'], alpha=alpha, chains=chains,
+                                  seed=seed)
+        return BatchResult(res['summary'].cpu().numpy(), res['p_value'].cpu().numpy(), alpha, args)
+
     def plot(self, panels: List[str] = ['original', 'pointwise', 'cumulative'], figsize: Tuple[int] = (10, 7),
              show: bool = True) -> None:
         plotter.plot(self.inferences, self.pre_data, self.post_data[self._mask], panels=panels,
@@ -84,3 +127,31 @@ class CausalImpact:
         self.summary_data = inferrer.summarize_posterior_inferences(
             self.inferences['post_preds_means'], post_masked, sims, self.alpha)
         self.p_value = inferrer.compute_p_value(sims, self.post_data.iloc[:, 0].sum())
+
+
+class BatchResult:
+    """Per-series summary tables and tail-area p-values of `CausalImpact.batch`."""
+
+    def __init__(self, summary: np.ndarray, p_values: np.ndarray, alpha: float, model_args: Dict[str, Any]):
+        self._summary = summary            # [N, 10, 2]
+        self.p_values = p_values           # [N]
+        self.alpha = alpha
+        self.model_args = model_args
+
+    def __len__(self):
+        return self._summary.shape[0]
+
+    def summary_data(self, i: int) -> pd.DataFrame:
+        """The 10x2 frame of series i (same index / columns as `CausalImpact.summary_data`)."""
+        return pd.DataFrame(self._summary[i].astype(np.float64), columns=['average', 'cumulative'],
+                            index=inferrer.SUMMARY_INDEX)
+
+    def summary(self, i: int, output: str = 'summary', digits: int = 2) -> str:
+        return summarizer.summary(self.summary_data(i), float(self.p_values[i]), self.alpha, output, digits)
+
+    def to_frame(self) -> pd.DataFrame:
+        """One row per series: the 'average' column of every summary row, the cumulative effect and p."""
+        cols = {name: self._summary[:, r, 0] for r, name in enumerate(inferrer.SUMMARY_INDEX)}
+        cols['cum_abs_effect'] = self._summary[:, 4, 1]
+        cols['p_value'] = self.p_values
+        return pd.DataFrame(cols)
