@@ -117,29 +117,42 @@ __device__ __forceinline__ uint32_t pick_draw(uint32_t sample_id, uint32_t strea
   return (uint32_t)(j < G ? j : G - 1);
 }
 
-// pre_sims[n][i][t] for 4 consecutive t per thread.
-__global__ void k_onestep_sample(int N, int G, int T, int nsamp, uint64_t seed, const float* __restrict__ pm,
-                                 const float* __restrict__ pv, const float* __restrict__ mu_sig,
-                                 float* __restrict__ sims) {
-  const int TQ = (T + 3) / 4;
-  const long total = (long)N * nsamp * TQ;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int tq = (int)(idx % TQ);
-  const long si = idx / TQ;  // n * nsamp + i
-  const int n = (int)(si / nsamp);
+// pre_sims[n][i][t]: 128 samples of one series per CTA, time tiled by 32 through shared memory.  The
+// lanes of a warp read the (mean, variance) of their picked draws of the SAME series and step (<= G
+// adjacent floats: a few sectors, L1-resident) and the [nsamp][T] rows are written as full 128 B lines.
+__global__ void __launch_bounds__(128)
+k_onestep_sample(int N, int G, int T, int nsamp, uint64_t seed, const float* __restrict__ pm,
+                 const float* __restrict__ pv, const float* __restrict__ mu_sig, float* __restrict__ sims) {
+  __shared__ float tile[128][33];
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * 128 + threadIdx.x;
   const long B = (long)N * G;
+  const long si = (long)n * nsamp + (i < nsamp ? i : 0);
   const long b = (long)n * G + pick_draw((uint32_t)si, 0u, G, seed);
-  const f32x4 z = philox_normal4((uint32_t)si, (uint32_t)tq, 0u, TAG_ONESTEP, seed);
-  const float zz[4] = {z.x, z.y, z.z, z.w};
   const float mu = mu_sig ? mu_sig[n] : 0.f, sg = mu_sig ? mu_sig[N + n] : 1.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int tn = min(32, T - t0);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int t = tq * 4 + q;
-    if (t < T) {
-      const float v = fmaf(sqrtf(pv[(long)t * B + b]), zz[q], pm[(long)t * B + b]);
-      sims[si * T + t] = fmaf(v, sg, mu);
+    for (int q4 = 0; q4 < 8; ++q4) {
+      // counter = (sample, time quad): the same stream as one Philox call per 4 consecutive steps
+      const f32x4 z = philox_normal4((uint32_t)si, (uint32_t)((t0 >> 2) + q4), 0u, TAG_ONESTEP, seed);
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = q4 * 4 + e;
+        if (q < tn) {
+          const long o = (long)(t0 + q) * B + b;
+          tile[threadIdx.x][q] = fmaf(fmaf(sqrtf(pv[o]), zz[e], pm[o]), sg, mu);
+        }
+      }
     }
+    __syncthreads();
+    for (int row = warp; row < 128; row += 4) {
+      const int ii = blockIdx.x * 128 + row;
+      if (ii < nsamp && lane < tn) sims[((long)n * nsamp + ii) * T + t0 + lane] = tile[row][lane];
+    }
+    __syncthreads();
   }
 }
 
@@ -315,8 +328,7 @@ int ci_onestep_sample(const ci_layout* L, const float* d_pred_mean, const float*
   CI_CHECK_ARG(nsamp >= 0 && (nsamp == 0 || d_pre_sims), "d_pre_sims is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (nsamp > 0) {
-    const long total = (long)L->N * nsamp * ((L->T + 3) / 4);
-    k_onestep_sample<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L->N, L->G, L->T, nsamp, seed, d_pred_mean,
+    k_onestep_sample<<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(L->N, L->G, L->T, nsamp, seed, d_pred_mean,
                                                                       d_pred_var, d_mu_sig, d_pre_sims);
   }
   if (d_pre_mean) {
