@@ -26,7 +26,7 @@
 #include "ci_params.cuh"
 
 #define CI_TC 4          // time steps per chunk
-#define CI_TAPE_AHEAD 4  // reverse sweep: L2 prefetch distance of the tape, in steps
+#define CI_TAPE_AHEAD 8  // reverse sweep: L2 prefetch distance of the tape, in steps
 
 namespace ci {
 
@@ -224,7 +224,6 @@ struct EffLane {
   float acc = 0.f, comp = 0.f;
   int nobs = 0;
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
-  float cur[D], nxt[D];
 
   CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, float* sr_, float* tape, int tstep_, float R_, float ql_,
                 float qd_)
@@ -343,17 +342,17 @@ struct EffLane {
     tp += tstep;
   }
 
-  // tp points at the entry of the step being processed (already held in `cur`).
+  // tp points at the entry of the step being processed; it was pulled into L2 CI_TAPE_AHEAD steps ago.
   template <int C>
   CI_HD float bwd_step(bool more, bool far) {
-    if (more) {   // request the entry of the previous step before the arithmetic ...
+    float cur[D];
 #pragma unroll
-      for (int q = 0; q < D; ++q) nxt[q] = (tp - tstep)[q * TQ];
-    }
-    if (far) {    // ... and pull the entry CI_TAPE_AHEAD steps back from HBM into L2
+    for (int q = 0; q < D; ++q) cur[q] = tp[q * TQ];
+    if (far) {    // pull the entry CI_TAPE_AHEAD steps back from HBM into L2
 #pragma unroll
       for (int q = 0; q < D; ++q) prefetch_l2((tp - CI_TAPE_AHEAD * tstep) + q * TQ);
     }
+    (void)more;
     eb_predict_adj<S, C>(st, qlb, qdb);
     float rb = 0.f;
     const float v = cur[S];
@@ -369,8 +368,6 @@ struct EffLane {
       const float s = g[0] + g[1 + C] + R;
       rb = eb_update_adj<S, C>(st, g, s, v, Rb);
     }
-#pragma unroll
-    for (int q = 0; q < D; ++q) cur[q] = nxt[q];
     tp -= tstep;
     return rb;
   }
@@ -430,11 +427,6 @@ CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __re
   for (int i = 0; i < EState<S>::NP; ++i) L.st.P[i] = 0.f;
   sr[0] = 0.f; sr[1] = 0.f; sr[2] = 0.f; sr[3] = 0.f;
   L.tp -= tstep;  // entry of step T-1
-#pragma unroll
-  for (int q = 0; q < S + 1; ++q) {
-    L.cur[q] = L.tp[q * TQ];
-    L.nxt[q] = 0.f;
-  }
   L.backward();
   params_backward_lane(u, ld, k, S, sc, scld, sb, SBLD, L.Rb, L.qlb, L.qdb, grad);
   *logp_out = ll + ls.lp0;
