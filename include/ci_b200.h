@@ -169,6 +169,19 @@ int ci_reduce_summary(const ci_layout* L, const float* d_y_post, const float* d_
                       const float* d_post_sims, int32_t nsamp, float alpha, float* d_summary,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- component decomposition ----------------------------------------------
+ * Replaces: tfp.sts.decompose_by_component / decompose_forecast_by_component as the reference's
+ * notebook applies them to ci.model / ci.model_samples (notebooks/getting_started.ipynb:125,144).
+ * L->G = posterior draws per series.  Outputs are mixtures over the draws, in MODEL units:
+ *   d_comp_mean, d_comp_sd  [3][N][W]   components: 0 LocalLevel, 1 regression (X_t beta), 2 Seasonal
+ *   W = T (smoothed pre-period marginals) or Tf (forecast marginals); absent components are zero. */
+size_t ci_decompose_workspace_bytes(const ci_layout* L);
+int ci_decompose_by_component(const ci_layout* L, const ci_data* D, const float* d_u, float* d_comp_mean,
+                              float* d_comp_sd, void* d_workspace, size_t workspace_bytes, void* stream);
+int ci_decompose_forecast(const ci_layout* L, const ci_data* D, const float* d_u, const float* d_fstate,
+                          float* d_comp_mean, float* d_comp_sd, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* Kernel launches one ci_kalman_logp_grad call enqueues (1: the evaluation is a single fused kernel). */
 int ci_eval_num_kernels(const ci_layout* L);
 

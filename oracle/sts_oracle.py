@@ -710,3 +710,87 @@ def p_value(sims, post_sum):
     """compute_p_value (inferences.py:397-408): strict inequalities, /(n+1)."""
     s = sims.sum(axis=1)
     return min(np.sum(s > post_sum), np.sum(s < post_sum)) / (len(sims) + 1)
+
+
+# ----------------------------------------------------------------------------------------
+# Component decomposition (tfp.sts.decompose_by_component / decompose_forecast_by_component, used
+# by the reference's notebook: notebooks/getting_started.ipynb:125,144) -- Rauch-Tung-Striebel
+# smoother over the dense model, per posterior draw, then the mixture over draws.
+# ----------------------------------------------------------------------------------------
+def _mixture_moments(mean_jt: torch.Tensor, var_jt: torch.Tensor, G: int):
+    """[N*G, W] per-draw moments -> mixture mean / stddev [N, W]."""
+    NG, W = mean_jt.shape
+    m = mean_jt.view(NG // G, G, W)
+    v = var_jt.view(NG // G, G, W)
+    mix_mean = m.mean(dim=1)
+    mix_var = (v + m * m).mean(dim=1) - mix_mean * mix_mean
+    return mix_mean, torch.sqrt(torch.clamp(mix_var, min=0.0))
+
+
+def smooth_components(prob: Problem, u_draws: torch.Tensor, series: torch.Tensor, G: int):
+    """Smoothed component marginals.  Returns dict name -> (mean[N,T], stddev[N,T]) with names
+    'LocalLevel', 'SparseLinearRegression' (if k > 0), 'Seasonal' (if S > 1)."""
+    L = prob.L
+    th, _ = constrain(u_draws, L, prob.st, series)
+    ssm = DenseSSM(th, L, prob.st, series)
+    off = residuals(prob, th, series, 0, L.T)
+    resid = prob.y[series] - off
+    B, T = resid.shape
+    d = ssm.d
+    eye = torch.eye(d, dtype=ssm.dtype)
+    m, P = ssm.m0, ssm.P0
+    mp, Pp, mf, Pf = [], [], [], []
+    for t in range(T):
+        mp.append(m); Pp.append(P)
+        r_t = resid[:, t]
+        mask = torch.isnan(r_t)
+        r_safe = torch.where(mask, torch.zeros_like(r_t), r_t)
+        g = P @ ssm.H
+        s = g @ ssm.H + ssm.obs_var
+        v = r_safe - m @ ssm.H
+        K = g / s[:, None]
+        m_f = torch.where(mask[:, None], m, m + K * v[:, None])
+        P_f = torch.where(mask[:, None, None], P, P - K[:, :, None] * g[:, None, :])
+        mf.append(m_f); Pf.append(P_f)
+        Ft = ssm.F(t)
+        m = m_f @ Ft.T
+        P = Ft[None] @ P_f @ Ft.T[None] + ssm.Q(t)
+    ms, Ps = [None] * T, [None] * T
+    ms[T - 1], Ps[T - 1] = mf[T - 1], Pf[T - 1]
+    for t in range(T - 2, -1, -1):
+        Ft = ssm.F(t)
+        A = Pf[t] @ Ft.T[None]                                  # P_f F^T
+        J = torch.linalg.solve(Pp[t + 1], A.transpose(1, 2)).transpose(1, 2)   # A P_pred^-1 (P_pred symmetric)
+        ms[t] = mf[t] + (J @ (ms[t + 1] - mp[t + 1])[:, :, None])[:, :, 0]
+        Ps[t] = Pf[t] + J @ (Ps[t + 1] - Pp[t + 1]) @ J.transpose(1, 2)
+    ms = torch.stack(ms, 1)                                     # [B, T, d]
+    Ps = torch.stack(Ps, 1)                                     # [B, T, d, d]
+    out = {'LocalLevel': _mixture_moments(ms[:, :, 0], Ps[:, :, 0, 0], G)}
+    if L.k > 0:
+        reg = off - prob.st.mean[series][:, None]
+        out['SparseLinearRegression'] = _mixture_moments(reg, torch.zeros_like(reg), G)
+    if L.S > 1:
+        out['Seasonal'] = _mixture_moments(ms[:, :, 1], Ps[:, :, 1, 1], G)
+    return out
+
+
+def forecast_components(prob: Problem, u_draws: torch.Tensor, series: torch.Tensor, G: int):
+    """Per-component forecast marginals (prior propagation from the filtered state at T)."""
+    L = prob.L
+    _, _, m, P, th, ssm = one_step_predictive(prob, u_draws, series)
+    off = residuals(prob, th, series, L.T, L.T + L.Tf)
+    lm, lv, sm, sv = [], [], [], []
+    for t in range(L.Tf):
+        lm.append(m[:, 0]); lv.append(P[:, 0, 0])
+        if L.S > 1:
+            sm.append(m[:, 1]); sv.append(P[:, 1, 1])
+        Ft = ssm.F(L.T + t)
+        m = m @ Ft.T
+        P = Ft[None] @ P @ Ft.T[None] + ssm.Q(L.T + t)
+    out = {'LocalLevel': _mixture_moments(torch.stack(lm, 1), torch.stack(lv, 1), G)}
+    if L.k > 0:
+        reg = off - prob.st.mean[series][:, None]
+        out['SparseLinearRegression'] = _mixture_moments(reg, torch.zeros_like(reg), G)
+    if L.S > 1:
+        out['Seasonal'] = _mixture_moments(torch.stack(sm, 1), torch.stack(sv, 1), G)
+    return out

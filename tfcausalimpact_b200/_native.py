@@ -36,7 +36,7 @@ def lib():
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.ci_last_error_string.restype = ctypes.c_char_p
         for name in ('ci_eval_workspace_bytes', 'ci_vi_workspace_bytes', 'ci_hmc_workspace_bytes',
-                     'ci_predict_workspace_bytes', 'ci_reduce_workspace_bytes', 'ci_fstate_floats'):
+                     'ci_predict_workspace_bytes', 'ci_reduce_workspace_bytes', 'ci_fstate_floats', 'ci_decompose_workspace_bytes'):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = ctypes.c_size_t
     return _lib

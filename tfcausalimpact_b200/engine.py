@@ -185,6 +185,28 @@ class DeviceBatch:
                    nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
         return sims, mean
 
+    # ---- component decomposition -------------------------------------------------------------
+    def decompose(self, u, fstate=None):
+        """Mixture-over-draws component marginals [3, N, W] (mean, sd): smoothed over the observed
+        period (fstate=None, W = T) or forecast over the horizon (fstate given, W = Tf)."""
+        B = u.shape[1]
+        L = self.layout(B // self.N)
+        W = self.T if fstate is None else self.Tf
+        mean, sd = self._f32(3, self.N, W), self._f32(3, self.N, W)
+        nbytes = self.lib.ci_decompose_workspace_bytes(ctypes.byref(L))
+        if nbytes == 0:
+            raise nt.NativeError(f'component decomposition does not support nseasons={self.S}')
+        ws = self.workspace('dec', nbytes)
+        D = self.data()
+        if fstate is None:
+            self._call('ci_decompose_by_component', ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()),
+                       nt.ptr(mean), nt.ptr(sd), nt.ptr(ws), ctypes.c_size_t(ws.numel()), nt.stream_ptr())
+        else:
+            self._call('ci_decompose_forecast', ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()),
+                       nt.ptr(fstate), nt.ptr(mean), nt.ptr(sd), nt.ptr(ws), ctypes.c_size_t(ws.numel()),
+                       nt.stream_ptr())
+        return mean, sd
+
     # ---- reductions --------------------------------------------------------------------------
     def reduce_inferences(self, y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):
         return reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha)
