@@ -76,7 +76,7 @@ struct Cols {
 // One filter step on the shared-memory state.  Returns false when the step is masked.
 // Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
 template <int NC>
-__device__ __forceinline__ bool big_step(float* P, float* m, float* g, int D, int S, int c, bool change, float resid,
+__device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int c, bool change, float resid,
                                          float R, float ql, float qd, float& s, float& v, float& is, int lane) {
   const Cols<NC> cl(lane, D);
   const int J = S > 1 ? 1 + c : 0;
@@ -101,17 +101,24 @@ __device__ __forceinline__ bool big_step(float* P, float* m, float* g, int D, in
     for (int q = 0; q < NC; ++q)
       if (cl.ok[q]) m[cl.j[q]] = fmaf(gj[q], vis, m[cl.j[q]]);
   }
-#pragma unroll 4
-  for (int i = 0; i < D; ++i) {
-    const float nki = g[i] * nis;
-    const float qi = qq * drift_w(i, c, S);
+  // rows in batches of 4: all loads of a batch are issued before its stores, so shared-memory latency is
+  // paid once per batch instead of once per row (the compiler cannot reorder a load of P past a store to P)
+  for (int i0 = 0; i0 < D; i0 += 4) {
+    float p[4][NC], nki[4], qi[4];
 #pragma unroll
-    for (int q = 0; q < NC; ++q) {
-      if (cl.ok[q]) {
-        float p = P[i * D + cl.j[q]];
-        p = fmaf(nki, gj[q], p);
-        p = fmaf(qi, wj[q], p);
-        P[i * D + cl.j[q]] = p;
+    for (int e = 0; e < 4; ++e) {
+      const int i = i0 + e < D ? i0 + e : D - 1;
+      nki[e] = g[i] * nis;
+      qi[e] = qq * drift_w(i, c, S);
+#pragma unroll
+      for (int q = 0; q < NC; ++q) p[e][q] = P[i * D + cl.j[q]];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i0 + e < D) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q)
+          if (cl.ok[q]) P[(i0 + e) * D + cl.j[q]] = fmaf(qi[e], wj[q], fmaf(nki[e], gj[q], p[e][q]));
       }
     }
   }
