@@ -75,7 +75,7 @@ struct Cols {
 
 // One filter step on the shared-memory state.  Returns false when the step is masked.
 // Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
-template <int NC>
+template <int NC, int RB>
 __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int c, bool change, float resid,
                                          float R, float ql, float qd, float& s, float& v, float& is, int lane) {
   const Cols<NC> cl(lane, D);
@@ -101,12 +101,13 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
     for (int q = 0; q < NC; ++q)
       if (cl.ok[q]) m[cl.j[q]] = fmaf(gj[q], vis, m[cl.j[q]]);
   }
-  // rows in batches of 4: all loads of a batch are issued before its stores, so shared-memory latency is
+  // rows in batches of RB (4 when a lone warp per scheduler is latency-bound, 8 when many lanes keep the
+  // SM busy): all loads of a batch are issued before its stores, so shared-memory latency is
   // paid once per batch instead of once per row (the compiler cannot reorder a load of P past a store to P)
-  for (int i0 = 0; i0 < D; i0 += 4) {
-    float p[4][NC], nki[4], qi[4];
+  for (int i0 = 0; i0 < D; i0 += RB) {
+    float p[RB][NC], nki[RB], qi[RB];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < RB; ++e) {
       const int i = i0 + e < D ? i0 + e : D - 1;
       nki[e] = g[i] * nis;
       qi[e] = qq * drift_w(i, c, S);
@@ -114,7 +115,7 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
       for (int q = 0; q < NC; ++q) p[e][q] = P[i * D + cl.j[q]];
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < RB; ++e) {
       if (i0 + e < D) {
 #pragma unroll
         for (int q = 0; q < NC; ++q)
@@ -162,7 +163,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     const int c = S > 1 ? season_of(t, S, r) : 0;
     const float resid = big_resid(XY, L, n, t, beta, lane);
     float s, v, is;
-    const bool obs = big_step<NC>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    const bool obs = big_step<NC, 4>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
     float* te = tp + (long)t * (D + 1);
 #pragma unroll
     for (int q = 0; q < NC; ++q)
@@ -343,7 +344,7 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
     xb = warp_sum(xb);
     float s, v, is;
     const float hm = m[0] + (S > 1 ? m[1 + c] : 0.f);
-    big_step<NC>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    big_step<NC, 8>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
     if (lane == 0) {
       pred_mean[(long)t * B + b] = hm + mean + xb;
       pred_var[(long)t * B + b] = s;
