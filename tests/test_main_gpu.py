@@ -137,3 +137,26 @@ def test_custom_model_and_rejection():
     assert abs(ci.summary_data.loc['abs_effect', 'average'] - 4.9) < 0.5
     with pytest.raises(ValueError):
         _ci(data, [0, 69], [70, 99], model=object())
+
+
+def test_no_covariates_and_season_duration():
+    """Single-column data (no regression component) with nseasons=4, season_duration=3, and a
+    nseasons outside the register-resident set (9 -> warp-per-lane kernels) through the front door."""
+    rng = np.random.default_rng(5)
+    n = 180
+    level = np.cumsum(rng.normal(scale=0.05, size=n)) + 20
+    seas = np.repeat([1.0, -0.5, 0.3, -0.8], 3)
+    y = level + np.tile(seas, n // 12 + 1)[:n] + rng.normal(scale=0.2, size=n)
+    y[150:] += 1.5
+    df = pd.DataFrame({'y': y})
+    np.random.seed(3)
+    ci = _ci(df, [0, 149], [150, 179], model_args={'nseasons': 4, 'season_duration': 3, 'niter': 500})
+    assert [type(c).__name__ for c in ci.model.components] == ['LocalLevel', 'Seasonal']
+    assert list(ci.model_samples.keys()) == ['observation_noise_scale', 'LocalLevel/_level_scale', 'Seasonal/_drift_scale']
+    assert 0.8 < ci.summary_data.loc['abs_effect', 'average'] < 2.2
+    assert ci.p_value < 0.1
+    np.random.seed(4)
+    ci9 = _ci(df, [0, 149], [150, 179], model_args={'nseasons': 9, 'niter': 300, 'fit_method': 'hmc'})
+    assert np.isfinite(ci9.summary_data.values).all()
+    assert 0.5 < ci9.summary_data.loc['abs_effect', 'average'] < 2.5
+    assert 0 <= ci9.p_value <= 1
