@@ -265,9 +265,9 @@ def main():
     accept = float(stats[0].mean().item())
     finite = bool(torch.isfinite(draws_buf[:args.steps]).all().item())
     draws_per_s = world * B * args.steps / (ms * 1e-3)
-    # launches: per transition begin + L * (eval kernels + leap) + end; + reset, initial eval, stats
+    # launches: per transition begin + L * eval kernel (leapfrog kick/drift fused in) + end; + reset, initial eval, stats
     kern_per_eval = int(lib.ci_eval_num_kernels(ctypes.byref(db.layout(C)))) if hasattr(lib, 'ci_eval_num_kernels') else 5
-    launches = args.steps * (2 + LEAPFROG * (kern_per_eval + 1)) + 2 + kern_per_eval
+    launches = args.steps * (2 + LEAPFROG * kern_per_eval) + 2 + kern_per_eval
 
     # ---- dominant kernel alone: Kalman log-prob + gradient evaluation ------------------------------
     lp = torch.empty(B, dtype=torch.float32, device=dev)
@@ -320,7 +320,8 @@ def main():
         'peak_source': 'measured in this run (ci_bench_fma FFMA probe); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4',
         'frac_of_nominal': ach_tf / 74.4, 'ms_per_launch': eval_ms,
         'algorithmic_flops_per_launch': flops_per_eval, 'algorithmic_bytes_per_launch': bytes_per_eval,
-        'hbm': {'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
+        'hbm': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
+                'traffic': traffic, 'actual_traffic_frac': (traffic / (eval_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'},
     }
 
