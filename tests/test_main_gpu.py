@@ -160,3 +160,21 @@ def test_no_covariates_and_season_duration():
     assert np.isfinite(ci9.summary_data.values).all()
     assert 0.5 < ci9.summary_data.loc['abs_effect', 'average'] < 2.5
     assert 0 <= ci9.p_value <= 1
+
+
+def test_google_data_notebook_table_vi():
+    """Real-TFP known answer stored in the reference's notebook (getting_started.ipynb cells 70-71, 76;
+    tests/golden/NOTEBOOK_TABLES.md): prediction 120.16 (3.62) [113.72, 127.92], abs effect 36.07,
+    rel 30.02%, p 0.0."""
+    gdata = pd.read_csv(os.path.join(GOLD, 'google_data.csv'), index_col='date')
+    np.random.seed(11)
+    ci = _ci(gdata, ['2020-01-01', '2020-03-01'], ['2020-03-02', '2020-03-31'])
+    s = ci.summary_data
+    assert abs(s.loc['actual', 'average'] - 156.23) < 0.01
+    assert abs(s.loc['actual', 'cumulative'] - 4687.0) < 0.5
+    assert abs(s.loc['predicted', 'average'] - 120.16) < 2.5          # within 0.7 published s.d.
+    sd = (s.loc['predicted_upper', 'average'] - s.loc['predicted_lower', 'average']) / 3.92
+    assert 2.0 < sd < 6.0                                            # published 3.62
+    assert abs(s.loc['abs_effect', 'average'] - 36.07) < 2.5
+    assert abs(s.loc['rel_effect', 'average'] - 0.3002) < 0.03
+    assert ci.p_value < 0.01
