@@ -178,3 +178,20 @@ def test_google_data_notebook_table_vi():
     assert abs(s.loc['abs_effect', 'average'] - 36.07) < 2.5
     assert abs(s.loc['rel_effect', 'average'] - 0.3002) < 0.03
     assert ci.p_value < 0.01
+
+
+def test_volks_weekly_nseasons52():
+    """The notebook's weekly Volkswagen example (getting_started.ipynb cells 81, 88): a pandas Series,
+    nseasons=52 -> the warp-per-lane large-latent kernels, weekly DatetimeIndex regularisation."""
+    data = pd.read_csv(os.path.join(GOLD, 'volks_data.csv'), header=0, sep=' ', index_col='Date', parse_dates=True)
+    pre_period = [str(np.min(data.index.values)), '2015-09-13']
+    post_period = ['2015-09-20', str(np.max(data.index.values))]
+    np.random.seed(9)
+    ci = _ci(data.iloc[:, 0], pre_period, post_period, model_args={'nseasons': 52, 'fit_method': 'vi', 'niter': 500})
+    assert ci.model.components[1].num_seasons == 52
+    s = ci.summary_data
+    assert np.isfinite(s.values).all()
+    assert len(ci.inferences) == len(ci.pre_data) + len(ci.post_data)
+    # the emissions scandal: observed prices fall well below the counterfactual
+    assert s.loc['abs_effect', 'average'] < 0
+    assert s.loc['predicted_lower', 'average'] < s.loc['predicted', 'average'] < s.loc['predicted_upper', 'average']
