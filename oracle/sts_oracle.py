@@ -23,7 +23,8 @@ What pins it: (1) the dense construction below builds the seasonal change-of-bas
 numerically (effects->residuals, permutation, residuals->effects) exactly the way TFP documents
 them, independently of the closed forms the CUDA kernels use; (2) gradients come from torch
 autograd and are cross-checked against fp64 central finite differences in tests/; (3) end-to-end
-summaries are compared with the README / tests known answers (tests/golden/README_tables.json);
+summaries are compared with the README / notebook / tests known answers (tests/golden/NOTEBOOK_TABLES.md,
+tests/test_oracle_known_answers.py);
 (4) the deterministic reduction semantics are checked against the reference's own
 tests/test_inferences.py expectations.
 """
