@@ -46,7 +46,15 @@ typedef struct ci_layout {
   int32_t S;    /* nseasons (1 = no seasonal component; model.py:310) */
   int32_t r;    /* season_duration (model.py:313) */
   int32_t Tpad; /* padded length of the packed design matrix: multiple of 4, >= T + Tf */
+  int32_t flags; /* CI_FLAG_*; 0 = the default model of causalimpact/model.py:239-321 */
 } ci_layout;
+
+/* Wider model set for custom `model=` (causalimpact/main.py:186-252 examples).
+ * Layouts with flags != 0 run on the large-latent (warp-per-lane) kernels. */
+#define CI_FLAG_DENSE_REG 1        /* tfp.sts.LinearRegression (StudentT(5,0,10) weights) instead of Sparse */
+#define CI_FLAG_LLT 2              /* tfp.sts.LocalLinearTrend (level + slope) instead of LocalLevel       */
+#define CI_FLAG_OBS_LOGNORMAL 4    /* observation noise prior LogNormal(log(.01 sd), 2) (tfp.sts.Sum default) */
+#define CI_FLAG_LEVEL_LOGNORMAL 8  /* level scale prior LogNormal(log(.05 sd), 3) (tfp.sts.LocalLevel default) */
 
 /* Caller-owned device inputs shared by every call on one batch of series. */
 typedef struct ci_data {
@@ -61,6 +69,8 @@ const char* ci_last_error_string(void);
 /* Number of scalar parameters of the layout: 2 + (k ? 2 + 3k : 0) + (S > 1).
  * Order = tfp `model.parameters` (notebooks/getting_started.ipynb:2228-2236). */
 int ci_num_params(int32_t k, int32_t S);
+/* ... of a layout with flags (trend 1|2 scales, regression 2+3k | k weights). */
+int ci_num_params_layout(const ci_layout* L);
 
 /* Empirical statistics + prior hyper-parameters per series.
  * Replaces: tfp sts_util.empirical_statistics as used by LocalLevel/Seasonal/Sum, and

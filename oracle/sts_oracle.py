@@ -38,6 +38,11 @@ import numpy as np
 import torch
 
 LOG_2PI = math.log(2.0 * math.pi)
+# wider model set (tfp.sts defaults a custom `model=` gets; /root/reference/causalimpact/main.py:186-252)
+FLAG_DENSE_REG = 1        # tfp.sts.LinearRegression: weights ~ StudentT(5, 0, 10), identity bijector
+FLAG_LLT = 2              # tfp.sts.LocalLinearTrend: level/slope scales ~ LogNormal(log(.05 sd), 3)
+FLAG_OBS_LOGNORMAL = 4    # tfp.sts.Sum default observation_noise_scale prior LogNormal(log(.01 sd), 2)
+FLAG_LEVEL_LOGNORMAL = 8  # tfp.sts.LocalLevel default level_scale prior LogNormal(log(.05 sd), 3)
 # /root/reference/causalimpact/model.py:39
 K_LOCAL_LEVEL_PRIOR_SAMPLE_SIZE = 32
 # tfp.sts.SparseLinearRegression default `weights_prior_scale`; pinned by
@@ -59,14 +64,32 @@ class Layout:
     k: int            # number of covariates (0 => no regression component)
     S: int = 1        # nseasons (1 => no seasonal component)
     r: int = 1        # season_duration
+    flags: int = 0    # wider model set (custom `model=`): FLAG_* below
+
+    @property
+    def llt(self) -> bool:
+        return bool(self.flags & FLAG_LLT)
+
+    @property
+    def dense_reg(self) -> bool:
+        return bool(self.flags & FLAG_DENSE_REG)
+
+    @property
+    def nt(self) -> int:
+        """trend latent size: level (+ slope for LocalLinearTrend)"""
+        return 2 if self.llt else 1
 
     @property
     def d(self) -> int:
-        return 1 + (self.S - 1 if self.S > 1 else 0)
+        return self.nt + (self.S - 1 if self.S > 1 else 0)
+
+    @property
+    def nreg(self) -> int:
+        return 0 if self.k == 0 else (self.k if self.dense_reg else 2 + 3 * self.k)
 
     @property
     def P(self) -> int:
-        return 2 + (2 + 3 * self.k if self.k > 0 else 0) + (1 if self.S > 1 else 0)
+        return 1 + self.nt + self.nreg + (1 if self.S > 1 else 0)
 
     # offsets into the flat parameter vector (TFP `model.parameters` order)
     @property
@@ -78,24 +101,32 @@ class Layout:
         return 1
 
     @property
-    def i_gsv(self) -> int:
+    def i_slope(self) -> int:
         return 2
 
     @property
+    def i_reg(self) -> int:
+        return 1 + self.nt
+
+    @property
+    def i_gsv(self) -> int:
+        return self.i_reg
+
+    @property
     def i_gsn(self) -> int:
-        return 3
+        return self.i_reg + 1
 
     @property
     def i_lsv(self) -> int:
-        return 4
+        return self.i_reg + 2
 
     @property
     def i_lsn(self) -> int:
-        return 4 + self.k
+        return self.i_reg + 2 + self.k
 
     @property
     def i_wn(self) -> int:
-        return 4 + 2 * self.k
+        return self.i_reg + 2 + 2 * self.k
 
     @property
     def i_drift(self) -> int:
@@ -103,6 +134,8 @@ class Layout:
 
     def param_names(self) -> List[str]:
         names = ['observation_noise_scale', 'LocalLevel/_level_scale']
+        if self.flags != 0:
+            raise NotImplementedError('names of the wider model set live in tfcausalimpact_b200.model')
         if self.k > 0:
             names += ['SparseLinearRegression/_global_scale_variance',
                       'SparseLinearRegression/_global_scale_noncentered',
@@ -171,14 +204,19 @@ def constrain(u: torch.Tensor, L: Layout, st: SeriesStats, series: torch.Tensor
 
     Returns the constrained parameter dict (TFP names) and the forward log-det-Jacobian [B].
     Scale parameters use Scale(observed_stddev) o Softplus; horseshoe positives use Softplus;
-    noncentered weights are unconstrained.
+    noncentered / dense weights are unconstrained.
     """
     sd = st.sd[series]
     th: Dict[str, torch.Tensor] = {}
     th['observation_noise_scale'] = sd * softplus(u[:, L.i_obs])
     th['LocalLevel/_level_scale'] = sd * softplus(u[:, L.i_level])
     ldj = 2.0 * torch.log(sd) + log_sigmoid(u[:, L.i_obs]) + log_sigmoid(u[:, L.i_level])
-    if L.k > 0:
+    if L.llt:
+        th['LocalLinearTrend/_slope_scale'] = sd * softplus(u[:, L.i_slope])
+        ldj = ldj + torch.log(sd) + log_sigmoid(u[:, L.i_slope])
+    if L.k > 0 and L.dense_reg:
+        th['LinearRegression/_weights'] = u[:, L.i_reg:L.i_reg + L.k]
+    elif L.k > 0:
         th['SparseLinearRegression/_global_scale_variance'] = softplus(u[:, L.i_gsv])
         th['SparseLinearRegression/_global_scale_noncentered'] = softplus(u[:, L.i_gsn])
         th['SparseLinearRegression/_local_scale_variances'] = softplus(u[:, L.i_lsv:L.i_lsv + L.k])
@@ -196,6 +234,8 @@ def constrain(u: torch.Tensor, L: Layout, st: SeriesStats, series: torch.Tensor
 def unconstrain(th: Dict[str, torch.Tensor], L: Layout, st: SeriesStats, series: torch.Tensor
                 ) -> torch.Tensor:
     """Inverse of `constrain` (used to turn constrained draws back into kernel inputs)."""
+    assert L.flags == 0, 'default model only'
+
     def sp_inv(x):
         return x + torch.log(-torch.expm1(-x))
     sd = st.sd[series]
@@ -218,19 +258,39 @@ def _log_inv_gamma(x, a, b):
     return a_t * torch.log(b) - torch.lgamma(a_t) - (a_t + 1.0) * torch.log(x) - b / x
 
 
+def _log_lognormal(x, mu, sigma):
+    z = (torch.log(x) - mu) / sigma
+    return -torch.log(x) - math.log(sigma) - 0.5 * LOG_2PI - 0.5 * z * z
+
+
 def log_prior(th: Dict[str, torch.Tensor], L: Layout, st: SeriesStats, series: torch.Tensor
               ) -> torch.Tensor:
     """Sum of prior log-densities at the constrained values.  [B]
 
     sigma = sqrt(V), V ~ InvGamma(16, b): TransformedDistribution(InverseGamma, Power(.5))
-    (model.py:211-216, 234-235) => log p(sigma) = log IG(sigma^2) + log(2 sigma).
+    (model.py:211-216, 234-235) => log p(sigma) = log IG(sigma^2) + log(2 sigma).  With the
+    FLAG_* options the tfp.sts defaults of a custom model are used instead.
     """
     a = K_LOCAL_LEVEL_PRIOR_SAMPLE_SIZE / 2.0
     so = th['observation_noise_scale']
     sl = th['LocalLevel/_level_scale']
-    lp = _log_inv_gamma(so * so, a, st.obs_b[series]) + torch.log(2.0 * so)
-    lp = lp + _log_inv_gamma(sl * sl, a, st.level_b[series]) + torch.log(2.0 * sl)
-    if L.k > 0:
+    mu01 = st.drift_mu[series]                       # log(0.01 sd)
+    mu05 = mu01 + math.log(5.0)                      # log(0.05 sd)
+    if L.flags & FLAG_OBS_LOGNORMAL:
+        lp = _log_lognormal(so, mu01, 2.0)
+    else:
+        lp = _log_inv_gamma(so * so, a, st.obs_b[series]) + torch.log(2.0 * so)
+    if L.llt or (L.flags & FLAG_LEVEL_LOGNORMAL):
+        lp = lp + _log_lognormal(sl, mu05, 3.0)
+    else:
+        lp = lp + _log_inv_gamma(sl * sl, a, st.level_b[series]) + torch.log(2.0 * sl)
+    if L.llt:
+        lp = lp + _log_lognormal(th['LocalLinearTrend/_slope_scale'], mu05, 3.0)
+    if L.k > 0 and L.dense_reg:
+        w = th['LinearRegression/_weights']
+        c = math.lgamma(3.0) - math.lgamma(2.5) - 0.5 * math.log(5.0 * math.pi) - math.log(10.0)
+        lp = lp + (c - 3.0 * torch.log1p(w * w / 500.0)).sum(dim=1)
+    elif L.k > 0:
         half = torch.as_tensor(0.5, dtype=so.dtype)
         gsv = th['SparseLinearRegression/_global_scale_variance']
         gsn = th['SparseLinearRegression/_global_scale_noncentered']
@@ -242,14 +302,15 @@ def log_prior(th: Dict[str, torch.Tensor], L: Layout, st: SeriesStats, series: t
         lp = lp + _log_inv_gamma(lsv, 0.5, half).sum(dim=1) + (log_hn - 0.5 * lsn * lsn).sum(dim=1)
         lp = lp + (-0.5 * LOG_2PI - 0.5 * wn * wn).sum(dim=1)
     if L.S > 1:
-        sdr = th['Seasonal/_drift_scale']
-        z = (torch.log(sdr) - st.drift_mu[series]) / 3.0
-        lp = lp + (-torch.log(sdr) - math.log(3.0) - 0.5 * LOG_2PI - 0.5 * z * z)
+        lp = lp + _log_lognormal(th['Seasonal/_drift_scale'], mu01, 3.0)
     return lp
 
 
 def regression_weights(th: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """Horseshoe weights, formula pinned by /root/reference/tests/test_main.py:326-339.  [B, k]"""
+    """Horseshoe weights, formula pinned by /root/reference/tests/test_main.py:326-339.  [B, k]
+    (dense LinearRegression: the weights themselves)."""
+    if 'LinearRegression/_weights' in th:
+        return th['LinearRegression/_weights']
     global_scale = (th['SparseLinearRegression/_global_scale_noncentered'] *
                     torch.sqrt(th['SparseLinearRegression/_global_scale_variance']) *
                     WEIGHTS_PRIOR_SCALE)
@@ -283,40 +344,48 @@ class DenseSSM:
         dtype = th['observation_noise_scale'].dtype
         B = series.shape[0]
         d = L.d
+        nt = L.nt
         self.B, self.d, self.dtype = B, d, dtype
         self.obs_var = th['observation_noise_scale'] ** 2
         self.level_var = th['LocalLevel/_level_scale'] ** 2
         H = torch.zeros(d, dtype=dtype)
         H[0] = 1.0
-        F_change = torch.eye(d, dtype=dtype)
+        F_base = torch.eye(d, dtype=dtype)
         self.Q_base = torch.zeros(B, d, d, dtype=dtype)
         self.Q_base[:, 0, 0] = self.level_var
-        self.Q_change = self.Q_base.clone()
         m0 = torch.zeros(B, d, dtype=dtype)
         m0[:, 0] = st.y0c[series]
         s0 = torch.abs(st.y0c[series]) + st.sd[series]
         P0 = torch.zeros(B, d, d, dtype=dtype)
         P0[:, 0, 0] = s0 * s0
+        if L.llt:
+            # tfp.sts.LocalLinearTrend: level' = level + slope + N(0, level_scale^2), slope' = slope +
+            # N(0, slope_scale^2); initial slope ~ N(0, observed_stddev^2)
+            F_base[0, 1] = 1.0
+            self.Q_base[:, 1, 1] = th['LocalLinearTrend/_slope_scale'] ** 2
+            P0[:, 1, 1] = st.sd[series] ** 2
+        F_change = F_base.clone()
+        self.Q_change = self.Q_base.clone()
         if L.S > 1:
             S = L.S
             e2r, r2e = _seasonal_basis(S, dtype)
             perm = np.concatenate([np.arange(1, S), [0]])
             perm_m = torch.as_tensor(np.eye(S)[perm], dtype=dtype)
             A = e2r @ perm_m @ r2e                       # (S-1)x(S-1)
-            F_change[1:, 1:] = A
+            F_change[nt:, nt:] = A
             h_eff = torch.zeros(1, S, dtype=dtype)
             h_eff[0, 0] = 1.0
-            H[1:] = (h_eff @ r2e)[0]
+            H[nt:] = (h_eff @ r2e)[0]
             drift = th['Seasonal/_drift_scale']
-            self.Q_change[:, 1:, 1:] = ((drift / S) ** 2)[:, None, None] * torch.ones(S - 1, S - 1, dtype=dtype)
+            self.Q_change[:, nt:, nt:] = ((drift / S) ** 2)[:, None, None] * torch.ones(S - 1, S - 1, dtype=dtype)
             # initial effects prior Normal(y0c, |y0c|+sd) per effect -> residual space
             mean_eff = st.y0c[series][:, None] * torch.ones(1, S, dtype=dtype)
-            m0[:, 1:] = mean_eff @ e2r.T
+            m0[:, nt:] = mean_eff @ e2r.T
             cov_res = e2r @ e2r.T
-            P0[:, 1:, 1:] = (s0 * s0)[:, None, None] * cov_res
+            P0[:, nt:, nt:] = (s0 * s0)[:, None, None] * cov_res
         self.H = H
         self.F_change = F_change
-        self.F_id = torch.eye(d, dtype=dtype)
+        self.F_id = F_base
         self.m0, self.P0 = m0, P0
 
     def F(self, t: int) -> torch.Tensor:

@@ -76,3 +76,43 @@ def test_linearity_property_full_size():
     scale = grads[1].abs().max()
     assert torch.all(torch.isfinite(grads[1]))
     assert (mid - grads[1]).abs().max() <= 2e-4 * scale
+
+
+# wider model set (custom `model=`): LocalLinearTrend, dense LinearRegression, tfp.sts default priors
+GEN_CASES = [
+    # flags, S, r, k, T, nan_frac, N, G
+    (O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 1, 1, 3, 60, 0.0, 3, 2),      # notebook cell 44 shape
+    (O.FLAG_LLT | O.FLAG_OBS_LOGNORMAL, 7, 1, 0, 70, 0.1, 2, 3),                         # main.py:191-193 shape
+    (O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL | O.FLAG_LEVEL_LOGNORMAL, 4, 2, 4, 50, 0.05, 2, 2),
+    (O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 12, 1, 2, 64, 0.0, 2, 2),
+    (O.FLAG_OBS_LOGNORMAL, 1, 1, 2, 45, 0.0, 3, 1),                                      # sparse + LogNormal noise prior
+    (O.FLAG_LLT, 3, 1, 40, 40, 0.0, 1, 2),
+]
+
+
+@pytest.mark.parametrize('flags,S,r,k,T,nan_frac,N,G', GEN_CASES)
+def test_wider_model_set_logp_grad_matches_oracle(flags, S, r, k, T, nan_frac, N, G):
+    from tfcausalimpact_b200.engine import DeviceBatch
+    Tf = 7
+    L = O.Layout(T, Tf, k, S, r, flags)
+    y, _, X = synth_problem(N, T, Tf, k, S, r, seed=S * 10 + k + flags, nan_frac=nan_frac)
+    prob = O.Problem.build(y, X, L, dtype=torch.float64)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S, season_duration=r, flags=flags)
+    assert db.P == L.P
+    rng = np.random.default_rng(2)
+    B = N * G
+    u = (rng.normal(size=(L.P, B)) * 0.6).astype(np.float32)
+    u[0] -= 1.0
+    u[1:1 + L.nt] -= 2.0
+    lp, g = db.logp_grad(torch.as_tensor(u).cuda())
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    series = torch.arange(B) // G
+    lpo, go = O.target_log_prob_and_grad(prob, torch.tensor(u.T.astype(np.float64)), series)
+    lpo, go = lpo.numpy(), go.numpy().T
+    np.testing.assert_allclose(lp, lpo, rtol=1e-4)
+    gmax = np.abs(go).max(axis=0, keepdims=True)
+    assert np.all(np.abs(g - go) <= 1e-4 * np.abs(go) + 1e-5 * gmax)
+    # constrain / unconstrain round trip of the generic parameter block
+    ud = torch.as_tensor(u).cuda()
+    th = db.constrain(ud)
+    np.testing.assert_allclose(db.unconstrain(th).cpu().numpy(), u, rtol=2e-4, atol=2e-4)

@@ -195,3 +195,33 @@ def test_volks_weekly_nseasons52():
     # the emissions scandal: observed prices fall well below the counterfactual
     assert s.loc['abs_effect', 'average'] < 0
     assert s.loc['predicted_lower', 'average'] < s.loc['predicted', 'average'] < s.loc['predicted_upper', 'average']
+
+
+def test_custom_model_local_linear_trend_and_linear_regression():
+    """The custom-model examples of the reference's docs (causalimpact/main.py:239-252, notebook
+    cell 44): LocalLinearTrend + LinearRegression built on standardised data, passed as `model=`."""
+    from tfcausalimpact_b200 import model as M
+    from tfcausalimpact_b200.misc import standardize
+    data = pd.read_csv(os.path.join(GOLD, 'arma_data.csv'))[['y', 'X']].astype(np.float32)
+    data.iloc[70:, 0] += 5
+    normed = (data - data.iloc[:70].mean()) / data.iloc[:70].std(ddof=0)
+    obs = normed.iloc[:70, 0]
+    model = M.Sum([M.LocalLinearTrend(observed_time_series=obs), M.LinearRegression(design_matrix=normed.iloc[:, 1:])],
+                  observed_time_series=obs)
+    assert model.param_names() == ['observation_noise_scale', 'LocalLinearTrend/_level_scale',
+                                   'LocalLinearTrend/_slope_scale', 'LinearRegression/_weights']
+    np.random.seed(6)
+    ci = _ci(data, [0, 69], [70, 99], model=model, model_args={'fit_method': 'hmc'})
+    assert isinstance(ci.model_samples, list) and len(ci.model_samples) == 4
+    assert tuple(ci.model_samples[3].shape) == (100, 1)
+    # notebook cell 45 (same model on a random arma draw): effect recovered with a wide interval
+    assert abs(ci.summary_data.loc['abs_effect', 'average'] - 5.0) < 1.5
+    assert ci.summary_data.loc['abs_effect_lower', 'average'] < ci.summary_data.loc['abs_effect', 'average']
+    # trend + seasonal (main.py:191-193)
+    model2 = M.Sum([M.LocalLinearTrend(observed_time_series=obs), M.Seasonal(num_seasons=7, observed_time_series=obs)],
+                   observed_time_series=obs)
+    np.random.seed(7)
+    ci2 = _ci(data[['y']], [0, 69], [70, 99], model=model2)
+    assert np.isfinite(ci2.summary_data.values).all()
+    with pytest.raises(ValueError):
+        M.Sum([M.LocalLevel(), M.LocalLinearTrend()], observed_time_series=obs)

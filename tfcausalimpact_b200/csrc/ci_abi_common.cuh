@@ -8,6 +8,7 @@
 #include "ci_core.cuh"
 #include "ci_dispatch.cuh"
 #include "ci_params.cuh"
+#include "ci_params_gen.cuh"
 
 namespace ci {
 
@@ -35,9 +36,16 @@ inline int check_layout(const ci_layout* L) {
   if (L->N < 1 || L->G < 1 || L->T < 1 || L->Tf < 0 || L->k < 0 || L->S < 1 || L->r < 1)
     return fail(CI_ERR_INVALID_ARGUMENT, "layout has a non-positive dimension");
   if (L->S == 1 && L->r != 1) return fail(CI_ERR_INVALID_ARGUMENT, "season_duration > 1 needs nseasons > 1");
+  if (L->flags & ~15) return fail(CI_ERR_INVALID_ARGUMENT, "unknown layout flags");
   if (L->Tpad % 4 != 0 || L->Tpad < L->T + L->Tf)
     return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 4 and >= T + Tf");
   return CI_OK;
+}
+
+// default model on the register-resident kernels; everything else on the warp-per-lane path
+inline bool ci_reg_path(const ci_layout* L) { return L->flags == 0 && ci_reg_set(L->S); }
+inline int layout_num_params(const ci_layout* L) {
+  return L->flags == 0 ? num_params(L->k, L->S) : num_params_gen(L->k, L->S, L->flags);
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -71,7 +79,7 @@ struct EvalWs {
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   const size_t B = ((size_t)L->N * L->G + 31) / 32 * 32;   // whole warps (warp-blocked tape layout)
-  const size_t nt = ci_reg_path(L->S) ? (size_t)L->T * (L->S + 1) * B : big_tape_floats(L);
+  const size_t nt = ci_reg_path(L) ? (size_t)L->T * (L->S + 1) * B : big_tape_floats(L);
   if (ws && c) ws->tape = c->floats(nt);
   return align_up(nt * 4, 256);
 }

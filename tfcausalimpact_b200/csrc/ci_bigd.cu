@@ -28,18 +28,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// latent layout: [level | slope (LocalLinearTrend only) | e_0 .. e_{S-1} (S > 1 only)]
+__host__ __device__ __forceinline__ int big_nt(const ci_layout& L) { return (L.flags & CI_FLAG_LLT) ? 2 : 1; }
+__host__ __device__ __forceinline__ int big_D(const ci_layout& L) { return big_nt(L) + (L.S > 1 ? L.S : 0); }
+
 __device__ __forceinline__ int season_of(int t, int S, int r) { return (t / r) % S; }
 __device__ __forceinline__ bool season_change(int t, int S, int r) { return S > 1 && (t % r) == r - 1; }
 // drift-direction weight of state index i (0 = level) when season c was just observed
-__device__ __forceinline__ float drift_w(int i, int c, int S) { return i == 0 ? 0.f : (i == 1 + c ? (float)(1 - S) : 1.f); }
+// (so = index of the first seasonal effect)
+__device__ __forceinline__ float drift_w(int i, int c, int S, int so) {
+  return i < so ? 0.f : (i == so + c ? (float)(1 - S) : 1.f);
+}
 
-__device__ void big_init(float* P, float* m, int D, int S, float m0, float p0, int lane) {
+__device__ void big_init(float* P, float* m, int D, int S, int so, float m0, float p0, float sd, int lane) {
   const float off = S > 1 ? -p0 / (float)S : 0.f;
   for (int i = 0; i < D; ++i)
     for (int j = lane; j < D; j += 32) {
       float v = 0.f;
-      if (i == 0 || j == 0) v = (i == 0 && j == 0) ? p0 : 0.f;
-      else v = (i == j) ? p0 + off : off;
+      if (i < so || j < so) {
+        if (i == j) v = (i == 0) ? p0 : sd * sd;      // level: (|y0c| + sd)^2 ; slope: sd^2
+      } else {
+        v = (i == j) ? p0 + off : off;
+      }
       P[i * D + j] = v;
     }
   for (int j = lane; j < D; j += 32) m[j] = (j == 0) ? m0 : 0.f;
@@ -76,16 +86,16 @@ struct Cols {
 // One filter step on the shared-memory state.  Returns false when the step is masked.
 // Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
 template <int NC, int RB>
-__device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int c, bool change, float resid,
-                                         float R, float ql, float qd, float& s, float& v, float& is, int lane) {
+__device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int so, int c, bool change, float resid,
+                                         float R, float ql, float qs, float qd, float& s, float& v, float& is, int lane) {
   const Cols<NC> cl(lane, D);
-  const int J = S > 1 ? 1 + c : 0;
+  const int J = S > 1 ? so + c : 0;
   const bool obs = (resid == resid);
   float gj[NC], wj[NC];
 #pragma unroll
   for (int q = 0; q < NC; ++q) {
     gj[q] = cl.ok[q] ? P[cl.j[q] * D] + (S > 1 ? P[cl.j[q] * D + J] : 0.f) : 0.f;
-    wj[q] = drift_w(cl.j[q], c, S);
+    wj[q] = drift_w(cl.j[q], c, S, so);
     if (cl.ok[q]) g[cl.j[q]] = gj[q];
   }
   __syncwarp();
@@ -110,7 +120,7 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
     for (int e = 0; e < RB; ++e) {
       const int i = i0 + e < D ? i0 + e : D - 1;
       nki[e] = g[i] * nis;
-      qi[e] = qq * drift_w(i, c, S);
+      qi[e] = qq * drift_w(i, c, S, so);
 #pragma unroll
       for (int q = 0; q < NC; ++q) p[e][q] = P[i * D + cl.j[q]];
     }
@@ -123,6 +133,21 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
       }
     }
   }
+  __syncwarp();
+  if (so == 2) {   // LocalLinearTrend transition F = I + e_level e_slope^T:  P <- F P F^T,  m <- F m
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+      if (cl.ok[q]) P[cl.j[q]] += P[D + cl.j[q]];          // row 0 += row 1
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NC; ++q)
+      if (cl.ok[q]) P[cl.j[q] * D] += P[cl.j[q] * D + 1];  // column 0 += column 1
+    __syncwarp();
+    if (lane == 0) {
+      m[0] += m[1];
+      P[D + 1] += qs;
+    }
+  }
   if (lane == 0) P[0] += ql;
   __syncwarp();
   return obs;
@@ -133,7 +158,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
            float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
-  const int S = L.S, D = S > 1 ? S + 1 : 1, k = L.k, T = L.T, r = L.r;
+  const int S = L.S, so = big_nt(L), D = big_D(L), k = L.k, T = L.T, r = L.r;
   const long B = (long)L.N * L.G;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long b = (long)blockIdx.x * BIG_WARPS + w;
@@ -149,12 +174,17 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   float* beta = gb + D;
   float* scal = beta + (k > 0 ? k : 1);
   if (lane == 0) {
-    const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
-    scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0;
+    if (L.flags == 0) {
+      const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = 0.f;
+    } else {
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = ls.qs;
+    }
   }
   __syncwarp();
-  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3];
-  big_init(P, m, D, S, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], lane);
+  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3], qs = scal[4];
+  big_init(P, m, D, S, so, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
   const Cols<NC> cl(lane, D);
   float* tp = tape + b * (long)T * (D + 1);
   float acc = 0.f, comp = 0.f;
@@ -163,7 +193,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     const int c = S > 1 ? season_of(t, S, r) : 0;
     const float resid = big_resid(XY, L, n, t, beta, lane);
     float s, v, is;
-    const bool obs = big_step<NC, 4>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    const bool obs = big_step<NC, 4>(P, m, g, D, S, so, c, season_change(t, S, r), resid, R, ql, qs, qd, s, v, is, lane);
     float* te = tp + (long)t * (D + 1);
 #pragma unroll
     for (int q = 0; q < NC; ++q)
@@ -186,7 +216,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   for (int j = lane; j < D; j += 32) mb[j] = 0.f;
   for (int j = lane; j < k; j += 32) beta[j] = 0.f;   // becomes beta_bar
   __syncwarp();
-  float Rb = 0.f, qlb = 0.f, qdb = 0.f;
+  float Rb = 0.f, qlb = 0.f, qsb = 0.f, qdb = 0.f;
   const int stride = (k + 1) * CI_TC;
   // software-pipelined tape reads: the entry of step t-1 is requested before step t is processed
   float cur_g[NC], cur_v, nxt_g[NC], nxt_v = 0.f;
@@ -201,7 +231,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   }
   for (int t = T - 1; t >= 0; --t) {
     const int c = S > 1 ? season_of(t, S, r) : 0;
-    const int J = S > 1 ? 1 + c : 0;
+    const int J = S > 1 ? so + c : 0;
     if (t > 0) {
       const float* tn = tp + (long)(t - 1) * (D + 1);
       nxt_v = tn[D];
@@ -215,10 +245,22 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
       gj[q] = obs ? cur_g[q] : 0.f;
-      wj[q] = cl.ok[q] ? drift_w(cl.j[q], c, S) : 0.f;
+      wj[q] = cl.ok[q] ? drift_w(cl.j[q], c, S, so) : 0.f;
       if (cl.ok[q]) g[cl.j[q]] = gj[q];
     }
     qlb += Pb[0];
+    if (so == 2) {   // adjoint of the LocalLinearTrend transition: Pbar <- F^T Pbar F, mbar <- F^T mbar
+      qsb += Pb[D + 1];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+        if (cl.ok[q]) Pb[D + cl.j[q]] += Pb[cl.j[q]];            // row 1 += row 0
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+        if (cl.ok[q]) Pb[cl.j[q] * D + 1] += Pb[cl.j[q] * D];    // column 1 += column 0
+      if (lane == 0) mb[1] += mb[0];
+    }
     __syncwarp();
     // one sweep over Pbar gives both the adjoint of the drift term (w^T Pbar w) and Pg = Pbar g
     float col[NC], nac[NC];
@@ -228,7 +270,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
 #pragma unroll 4
       for (int i = 0; i < D; ++i) {
         const float gi = g[i];
-        const float wi = drift_w(i, c, S);
+        const float wi = drift_w(i, c, S, so);
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
           const float pb = Pb[i * D + cl.j[q]];
@@ -301,7 +343,8 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   }
   (void)gb;
   if (lane == 0) {
-    params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
+    if (L.flags == 0) params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
+    else params_backward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, Rb, qlb, qsb, qdb, grad + b);
     logp[b] = ll + lp0;
   }
 }
@@ -312,7 +355,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
              float* __restrict__ pred_mean, float* __restrict__ pred_var, float* __restrict__ fstate) {
   extern __shared__ __align__(16) float smem[];
-  const int S = L.S, D = S > 1 ? S + 1 : 1, k = L.k, T = L.T, r = L.r;
+  const int S = L.S, so = big_nt(L), D = big_D(L), k = L.k, T = L.T, r = L.r;
   const long B = (long)L.N * L.G;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long b = (long)blockIdx.x * BIG_WARPS + w;
@@ -326,13 +369,18 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
   float* beta = g + 3 * D;
   float* scal = beta + (k > 0 ? k : 1);
   if (lane == 0) {
-    const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
-    scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd;
+    if (L.flags == 0) {
+      const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = 0.f;
+    } else {
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = ls.qs;
+    }
   }
   __syncwarp();
-  const float R = scal[0], ql = scal[1], qd = scal[2];
+  const float R = scal[0], ql = scal[1], qd = scal[2], qs = scal[4];
   const float mean = sconst[SC_MEAN * L.N + n];
-  big_init(P, m, D, S, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], lane);
+  big_init(P, m, D, S, so, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
   for (int t = 0; t < T; ++t) {
     const int c = S > 1 ? season_of(t, S, r) : 0;
     const float resid = big_resid(XY, L, n, t, beta, lane);      // (y - mean) - X beta, NaN if masked
@@ -343,8 +391,8 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
     for (int j = lane; j < k; j += 32) xb = fmaf(beta[j], __ldg(xp + j * CI_TC), xb);
     xb = warp_sum(xb);
     float s, v, is;
-    const float hm = m[0] + (S > 1 ? m[1 + c] : 0.f);
-    big_step<NC, 8>(P, m, g, D, S, c, season_change(t, S, r), resid, R, ql, qd, s, v, is, lane);
+    const float hm = m[0] + (S > 1 ? m[so + c] : 0.f);
+    big_step<NC, 8>(P, m, g, D, S, so, c, season_change(t, S, r), resid, R, ql, qs, qd, s, v, is, lane);
     if (lane == 0) {
       pred_mean[(long)t * B + b] = hm + mean + xb;
       pred_var[(long)t * B + b] = s;
@@ -387,7 +435,7 @@ __device__ __forceinline__ uint32_t pick_draw_big(uint32_t sample_id, uint32_t s
 
 __global__ void k_forecast_mean_big(ci_layout L, const float* __restrict__ fstate, const float* __restrict__ off,
                                     float* __restrict__ pm) {
-  const int S = L.S, D = S > 1 ? S + 1 : 1;
+  const int S = L.S, so = big_nt(L), D = big_D(L);
   const long B = (long)L.N * L.G;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * L.Tf) return;
@@ -395,7 +443,7 @@ __global__ void k_forecast_mean_big(ci_layout L, const float* __restrict__ fstat
   const int t = (int)(idx / B);
   const float* fs = fstate + b * (long)(D + 2 * D * D);
   const int c = S > 1 ? season_of(L.T + t, S, L.r) : 0;
-  pm[idx] = fs[0] + (S > 1 ? fs[1 + c] : 0.f) + off[idx];
+  pm[idx] = fs[0] + (so == 2 ? (float)t * fs[1] : 0.f) + (S > 1 ? fs[so + c] : 0.f) + off[idx];
 }
 
 #define CI_BIG_MAXD 96
@@ -405,13 +453,14 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
                       const float* __restrict__ scal, const float* __restrict__ off,
                       const float* __restrict__ mu_sig, float* __restrict__ sims) {
   __shared__ float tile[128][33];
-  const int S = L.S, D = S > 1 ? S + 1 : 1, Tf = L.Tf, r = L.r;
+  const int S = L.S, so = big_nt(L), D = big_D(L), Tf = L.Tf, r = L.r;
   const int n = blockIdx.y;
   const int i = blockIdx.x * 128 + threadIdx.x;
   const long B = (long)L.N * L.G;
   const long si = (long)n * nsamp + (i < nsamp ? i : 0);
   const long b = (long)n * L.G + pick_draw_big((uint32_t)si, 1u, L.G, seed);
-  const float so = sqrtf(scal[0 * B + b]), sl = sqrtf(scal[1 * B + b]), sdr = sqrtf(scal[2 * B + b]);
+  const float sobs = sqrtf(scal[0 * B + b]), sl = sqrtf(scal[1 * B + b]), sdr = sqrtf(scal[2 * B + b]);
+  const float sslope = so == 2 ? sqrtf(scal[4 * B + b]) : 0.f;
   const float mu = mu_sig ? mu_sig[n] : 0.f, sg = mu_sig ? mu_sig[L.N + n] : 1.f;
   const float* fs = fstate + b * (long)(D + 2 * D * D);
   const float* Lc = fs + D + D * D;
@@ -433,13 +482,17 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
       const int t = t0 + q;
       const int c = S > 1 ? season_of(L.T + t, S, r) : 0;
       const f32x4 e = philox_normal4((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
-      const float yv = x[0] + (S > 1 ? x[1 + c] : 0.f) + off[(long)t * B + b] + so * e.x;
+      const float yv = x[0] + (S > 1 ? x[so + c] : 0.f) + off[(long)t * B + b] + sobs * e.x;
       tile[threadIdx.x][q] = fmaf(yv, sg, mu);
+      if (so == 2) {                   // level += slope ; slope random walk
+        x[0] += x[1];
+        x[1] = fmaf(sslope, e.w, x[1]);
+      }
       x[0] = fmaf(sl, e.y, x[0]);
       if (season_change(L.T + t, S, r)) {
         const float xi = sdr * e.z;
-        for (int a = 1; a < D; ++a) x[a] += xi;
-        x[1 + c] -= (float)S * xi;    // net -(S-1) xi on the season just observed
+        for (int a = so; a < D; ++a) x[a] += xi;
+        x[so + c] -= (float)S * xi;    // net -(S-1) xi on the season just observed
       }
     }
     __syncthreads();
@@ -452,22 +505,22 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
 }
 
 size_t big_smem_bytes(const ci_layout* L) {
-  const int D = L->S > 1 ? L->S + 1 : 1;
+  const int D = big_D(*L);
   return (size_t)BIG_WARPS * (2 * D * D + 4 * D + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
 }
 
 bool big_supported(const ci_layout* L) {
-  const int D = L->S > 1 ? L->S + 1 : 1;
+  const int D = big_D(*L);
   return D <= CI_BIG_MAXD && big_smem_bytes(L) <= 227 * 1024;
 }
 
 size_t big_tape_floats(const ci_layout* L) {
-  const size_t D = L->S > 1 ? L->S + 1 : 1;
+  const size_t D = big_D(*L);
   return (size_t)L->N * L->G * L->T * (D + 1);
 }
 
 size_t big_fstate_floats(const ci_layout* L) {
-  const size_t D = L->S > 1 ? L->S + 1 : 1;
+  const size_t D = big_D(*L);
   return D + 2 * D * D;
 }
 
@@ -486,7 +539,7 @@ int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, floa
   const size_t smem = big_smem_bytes(L);
   const long B = (long)L->N * L->G;
   const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
-  const int Dl = L->S > 1 ? L->S + 1 : 1;
+  const int Dl = big_D(*L);
 #define CI_BIG_EVAL(NC)                                                                                    \
   {                                                                                                        \
     if (int e = big_attr(k_eval_big<NC>, smem)) return e;                                                  \
@@ -503,7 +556,7 @@ int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, fl
   const size_t smem = big_smem_bytes(L);
   const long B = (long)L->N * L->G;
   const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
-  const int Dl = L->S > 1 ? L->S + 1 : 1;
+  const int Dl = big_D(*L);
 #define CI_BIG_FILTER(NC)                                                                              \
   {                                                                                                    \
     if (int e = big_attr(k_filter_big<NC>, smem)) return e;                                            \

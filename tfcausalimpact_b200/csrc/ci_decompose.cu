@@ -259,7 +259,7 @@ using namespace ci;
 extern "C" {
 
 size_t ci_decompose_workspace_bytes(const ci_layout* L) {
-  if (check_layout(L) || !ci_reg_path(L->S)) return 0;
+  if (check_layout(L) || !ci_reg_path(L)) return 0;
   const size_t a = dec_ws_floats(L, L->T, true, nullptr, nullptr);
   const size_t b = dec_ws_floats(L, L->Tf > 0 ? L->Tf : 1, false, nullptr, nullptr);
   return a > b ? a : b;
@@ -270,7 +270,7 @@ int ci_decompose_by_component(const ci_layout* L, const ci_data* D, const float*
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_comp_mean && d_comp_sd && d_workspace, "NULL pointer");
-  if (!ci_reg_path(L->S)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
+  if (!ci_reg_path(L)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
   if (workspace_bytes < dec_ws_floats(L, L->T, true, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", dec_ws_floats(L, L->T, true, nullptr, nullptr));
   cudaStream_t st = (cudaStream_t)stream;
@@ -294,7 +294,7 @@ int ci_decompose_forecast(const ci_layout* L, const ci_data* D, const float* d_u
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_fstate && d_comp_mean && d_comp_sd && d_workspace, "NULL pointer");
   CI_CHECK_ARG(L->Tf >= 1, "forecast horizon Tf must be >= 1");
-  if (!ci_reg_path(L->S)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
+  if (!ci_reg_path(L)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
   if (workspace_bytes < dec_ws_floats(L, L->Tf, false, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", dec_ws_floats(L, L->Tf, false, nullptr, nullptr));
   cudaStream_t st = (cudaStream_t)stream;

@@ -18,4 +18,4 @@
   }
 
 // nseasons served by the register-resident kernels (must match the cases above)
-static inline bool ci_reg_path(int S) { return (S >= 1 && S <= 7) || S == 12; }
+static inline bool ci_reg_set(int S) { return (S >= 1 && S <= 7) || S == 12; }

@@ -182,18 +182,28 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
   }
 }
 
-__global__ void k_params_forward(int N, int G, int k, int S, const float* __restrict__ sconst,
+__global__ void k_params_forward(int N, int G, int k, int S, int flags, const float* __restrict__ sconst,
                                  const float* __restrict__ u, float* __restrict__ beta,
                                  float* __restrict__ scal) {
   const long B = (long)N * G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / G);
-  LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, N, beta + b, B);
-  scal[0 * B + b] = ls.R;
-  scal[1 * B + b] = ls.ql;
-  scal[2 * B + b] = ls.qd;
-  scal[3 * B + b] = ls.lp0;
+  if (flags == 0) {
+    LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, N, beta + b, B);
+    scal[0 * B + b] = ls.R;
+    scal[1 * B + b] = ls.ql;
+    scal[2 * B + b] = ls.qd;
+    scal[3 * B + b] = ls.lp0;
+    scal[4 * B + b] = 0.f;
+  } else {
+    GenScalars ls = params_forward_gen(u + b, B, k, S, flags, sconst + n, N, beta + b, B);
+    scal[0 * B + b] = ls.R;
+    scal[1 * B + b] = ls.ql;
+    scal[2 * B + b] = ls.qd;
+    scal[3 * B + b] = ls.lp0;
+    scal[4 * B + b] = ls.qs;     // slope variance (LocalLinearTrend)
+  }
 }
 
 // out[t - t_lo][b] for t in [t_lo, t_hi):  with_y ? y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]
@@ -242,7 +252,8 @@ void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, flo
 void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
                            cudaStream_t st) {
   const long B = (long)L->N * L->G;
-  k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, D->d_sconst, d_u, beta, scal);
+  k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, L->flags, D->d_sconst, d_u, beta,
+                                                                scal);
 }
 
 template <int S, bool STAGED, bool EFF>
@@ -270,11 +281,11 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
                 const EvalWs& ws, cudaStream_t st, const LeapArgs* leap) {
   int rc = CI_OK;
   const LeapArgs lf = leap ? *leap : LeapArgs();
-  if (!ci_reg_path(L->S)) {   // large latent: warp-per-lane kernels + a separate leapfrog update
+  if (!ci_reg_path(L)) {   // large latent: warp-per-lane kernels + a separate leapfrog update
     if (int e = launch_eval_big(L, D, d_u, d_logp, d_grad, ws.tape, st)) return e;
     if (lf.pp) {
       const long B = (long)L->N * L->G;
-      k_leap<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(lf, num_params(L->k, L->S), B, d_grad);
+      k_leap<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(lf, layout_num_params(L), B, d_grad);
     }
     CI_CHECK_LAUNCH();
     return CI_OK;
@@ -366,13 +377,14 @@ __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const 
   XY[i] = v;
 }
 
-__global__ void k_constrain(int N, int G, int k, int S, const float* __restrict__ sconst,
+__global__ void k_constrain(int N, int G, int k, int S, int flags, const float* __restrict__ sconst,
                             const float* __restrict__ u, float* __restrict__ theta) {
   const long B = (long)N * G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / G);
-  params_constrain_lane(u + b, B, k, S, sconst[SC_SD * N + n], theta + b, B);
+  if (flags == 0) params_constrain_lane(u + b, B, k, S, sconst[SC_SD * N + n], theta + b, B);
+  else params_constrain_gen(u + b, B, k, S, flags, sconst[SC_SD * N + n], theta + b, B);
 }
 
 }  // namespace ci
@@ -384,6 +396,7 @@ extern "C" {
 int ci_version(void) { return 100; }
 const char* ci_last_error_string(void) { return last_error_buf(); }
 int ci_num_params(int32_t k, int32_t S) { return num_params(k, S); }
+int ci_num_params_layout(const ci_layout* L) { return L ? layout_num_params(L) : -1; }
 
 int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, float* d_sconst, void* stream) {
   if (int e = check_layout(L)) return e;
@@ -416,7 +429,7 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_logp && d_grad && d_workspace, "NULL pointer");
-  if (!ci_reg_path(L->S) && !big_supported(L))
+  if (!ci_reg_path(L) && !big_supported(L))
     return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_eval_workspace_bytes(L))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_eval_workspace_bytes(L));
@@ -430,7 +443,7 @@ int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* 
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_sconst && d_u && d_theta, "NULL pointer");
   const long B = (long)L->N * L->G;
-  k_constrain<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(L->N, L->G, L->k, L->S, D->d_sconst,
+  k_constrain<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(L->N, L->G, L->k, L->S, L->flags, D->d_sconst,
                                                                             d_u, d_theta);
   CI_CHECK_LAUNCH();
   return CI_OK;

@@ -32,7 +32,7 @@ struct ViWs {
 
 static size_t vi_ws_floats(const ci_layout* L, int units_per_series, ViWs* ws, Carver* c) {
   const size_t B = (size_t)L->N * L->G, U = (size_t)L->N * units_per_series;
-  const size_t P = num_params(L->k, L->S);
+  const size_t P = layout_num_params(L);
   size_t tot = 3 * align_up(P * B * 4, 256) + align_up(B * 4, 256) + align_up(4 * P * U * 4, 256);
   if (ws && c) {
     ws->u = c->floats(P * B);
@@ -158,7 +158,7 @@ enum { HL_LP = 0, HL_LPNEW, HL_H0, HL_LOGFAC, HL_LOGFAC_AVG, HL_ERRSUM, HL_ACC_W
 
 static size_t hmc_ws_floats(const ci_layout* L, HmcWs* ws, Carver* c) {
   const size_t B = (size_t)L->N * L->G;
-  const size_t P = num_params(L->k, L->S);
+  const size_t P = layout_num_params(L);
   size_t tot = 4 * align_up(P * B * 4, 256) + align_up(HL_N * B * 4, 256);
   if (ws && c) {
     ws->uu = c->floats(P * B);
@@ -279,7 +279,7 @@ int ci_vi_fit(const ci_layout* L, const ci_data* D, int32_t units_per_series, in
   CI_CHECK_ARG(units_per_series >= 1 && sample_size >= 1 && num_steps >= 0, "non-positive count");
   CI_CHECK_ARG(L->G == units_per_series * sample_size, "layout G must equal units_per_series * sample_size");
   CI_CHECK_ARG(learning_rate > 0.f && init_scale > 0.f, "learning_rate and init_scale must be positive");
-  if (!ci_reg_path(L->S) && !big_supported(L))
+  if (!ci_reg_path(L) && !big_supported(L))
     return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_vi_workspace_bytes(L, units_per_series))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_vi_workspace_bytes(L, units_per_series));
@@ -288,7 +288,7 @@ int ci_vi_fit(const ci_layout* L, const ci_data* D, int32_t units_per_series, in
   ViWs ws;
   vi_ws_floats(L, units_per_series, &ws, &c);
   const long B = (long)L->N * L->G, U = (long)L->N * units_per_series;
-  const int P = num_params(L->k, L->S);
+  const int P = layout_num_params(L);
   k_vi_init<<<nblk(U * P, 256), 256, 0, st>>>(U, P, seed, init_scale, d_mu, d_rho, ws.adam);
   for (int step = 0; step < num_steps; ++step) {
     k_vi_sample<<<nblk(B * P, 256), 256, 0, st>>>(B, U, P, sample_size, step, seed, d_mu, d_rho, ws.u, ws.xi);
@@ -328,7 +328,7 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
   CI_CHECK_ARG(num_adapt >= 0 && num_adapt <= num_warmup, "num_adapt must lie in [0, num_warmup]");
   CI_CHECK_ARG(num_results == 0 || d_draws, "d_draws is NULL");
   CI_CHECK_ARG(target_accept > 0.f && target_accept < 1.f, "target_accept must lie in (0, 1)");
-  if (!ci_reg_path(L->S) && !big_supported(L))
+  if (!ci_reg_path(L) && !big_supported(L))
     return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < ci_hmc_workspace_bytes(L))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", ci_hmc_workspace_bytes(L));
@@ -337,7 +337,7 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
   HmcWs ws;
   hmc_ws_floats(L, &ws, &c);
   const long B = (long)L->N * L->G;
-  const int P = num_params(L->k, L->S);
+  const int P = layout_num_params(L);
   const unsigned gl = nblk(B, 128);
   k_hmc_reset<<<gl, 128, 0, st>>>(B, ws.lane);
   // log-prob and gradient at the initial state (cached between transitions, as TFP does)

@@ -301,7 +301,7 @@ int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, fl
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_pred_mean && d_pred_var && d_fstate && d_workspace, "NULL pointer");
-  if (!ci_reg_path(L->S) && !big_supported(L))
+  if (!ci_reg_path(L) && !big_supported(L))
     return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < pred_ws_floats(L, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", pred_ws_floats(L, nullptr, nullptr));
@@ -309,7 +309,7 @@ int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, fl
   Carver c(d_workspace);
   PredWs ws;
   pred_ws_floats(L, &ws, &c);
-  if (!ci_reg_path(L->S)) {
+  if (!ci_reg_path(L)) {
     if (int e = launch_filter_big(L, D, d_u, d_pred_mean, d_pred_var, d_fstate, st)) return e;
     CI_CHECK_LAUNCH();
     return CI_OK;
@@ -348,7 +348,7 @@ int ci_forecast_sample(const ci_layout* L, const ci_data* D, const float* d_u, c
   CI_CHECK_ARG(d_u && d_fstate && d_workspace, "NULL pointer");
   CI_CHECK_ARG(L->Tf >= 1, "forecast horizon Tf must be >= 1");
   CI_CHECK_ARG(nsamp >= 0 && (nsamp == 0 || d_post_sims), "d_post_sims is NULL");
-  if (!ci_reg_path(L->S) && !big_supported(L))
+  if (!ci_reg_path(L) && !big_supported(L))
     return fail(CI_ERR_UNSUPPORTED, "nseasons=%d not supported by this build", L->S);
   if (workspace_bytes < fc_ws_floats(L, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", fc_ws_floats(L, nullptr, nullptr));
@@ -358,7 +358,7 @@ int ci_forecast_sample(const ci_layout* L, const ci_data* D, const float* d_u, c
   fc_ws_floats(L, &ws, &c);
   launch_params_forward(L, D, d_u, ws.beta, ws.scal, st);
   launch_offsets(L, D, ws.beta, ws.off, L->T, L->T + L->Tf, 0, st);
-  if (!ci_reg_path(L->S)) {
+  if (!ci_reg_path(L)) {
     launch_forecast_big(L, d_fstate, ws.scal, ws.off, ws.pm, d_mu_sig, nsamp, seed, nsamp > 0 ? d_post_sims : nullptr, st);
   } else {
     CI_DISPATCH_S(L->S, (launch_forecast<S_>(L, ws, d_fstate, d_mu_sig, nsamp, seed, nsamp > 0 ? d_post_sims : nullptr, st)));
@@ -377,6 +377,6 @@ int ci_forecast_sample(const ci_layout* L, const ci_data* D, const float* d_u, c
  * [nfs][B] lane-fastest for the register-resident kernels, lane-contiguous [B][nfs] otherwise). */
 extern "C" size_t ci_fstate_floats(const ci_layout* L) {
   if (check_layout(L)) return 0;
-  if (ci_reg_path(L->S)) return (size_t)L->S + (size_t)L->S * (L->S + 1);
+  if (ci_reg_path(L)) return (size_t)L->S + (size_t)L->S * (L->S + 1);
   return big_fstate_floats(L);
 }

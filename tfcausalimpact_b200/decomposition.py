@@ -24,7 +24,8 @@ class ComponentDist:
 def _components(model, mean, sd):
     out = OrderedDict()
     for comp in model.components:
-        row = {cimodel.LocalLevel: 0, cimodel.SparseLinearRegression: 1, cimodel.Seasonal: 2}[type(comp)]
+        row = {cimodel.LocalLevel: 0, cimodel.LocalLinearTrend: 0, cimodel.SparseLinearRegression: 1,
+               cimodel.LinearRegression: 1, cimodel.Seasonal: 2}[type(comp)]
         out[comp] = ComponentDist(mean[row, 0], sd[row, 0])
     return out
 

@@ -111,9 +111,34 @@ class LocalLevel(Component):
     def __init__(self, level_scale_prior: Optional[Prior] = None, observed_time_series=None, name='LocalLevel'):
         self.name = name
         if level_scale_prior is None:
-            level_scale_prior = build_bijector(build_inv_gamma_sd_prior(0.01))
+            # tfp.sts.LocalLevel default: LogNormal(log(.05 sd), 3)
+            level_scale_prior = Prior('LogNormal', {'loc': float('nan'), 'scale': 3.0})
         self.level_scale_prior = level_scale_prior
         self.parameters = [Parameter('level_scale', level_scale_prior, 'Scale(sd_y) o Softplus')]
+
+
+class LocalLinearTrend(Component):
+    """Level + slope random walks (tfp.sts.LocalLinearTrend with its default priors: both scales
+    LogNormal(log(.05 sd), 3), initial slope N(0, sd^2)) -- the trend of the custom-model examples in
+    the reference's docs (causalimpact/main.py:191,217,246)."""
+
+    def __init__(self, observed_time_series=None, name='LocalLinearTrend'):
+        self.name = name
+        ln = Prior('LogNormal', {'loc': float('nan'), 'scale': 3.0})
+        self.parameters = [Parameter('level_scale', ln, 'Scale(sd_y) o Softplus'),
+                           Parameter('slope_scale', ln, 'Scale(sd_y) o Softplus')]
+
+
+class LinearRegression(Component):
+    """Dense regression with tfp.sts.LinearRegression's default prior: weights ~ StudentT(5, 0, 10)."""
+
+    def __init__(self, design_matrix, name='LinearRegression'):
+        self.name = name
+        if isinstance(design_matrix, pd.DataFrame):
+            design_matrix = design_matrix.values
+        self.design_matrix = design_matrix if isinstance(design_matrix, DesignMatrix) else DesignMatrix(design_matrix)
+        k = self.design_matrix.shape[1]
+        self.parameters = [Parameter('weights', Prior('StudentT', {'df': 5.0, 'loc': 0.0, 'scale': 10.0}), 'Identity', (k,))]
 
 
 class SparseLinearRegression(Component):
@@ -148,8 +173,10 @@ class Seasonal(Component):
 
 
 class Sum:
-    """Additive structural time-series model = the fixed layout the kernels implement:
-    LocalLevel [+ SparseLinearRegression] [+ Seasonal] + observation noise."""
+    """Additive structural time-series model the kernels implement: one trend (LocalLevel |
+    LocalLinearTrend) [+ one regression (SparseLinearRegression | LinearRegression)] [+ Seasonal] +
+    observation noise.  Built without `observation_noise_scale_prior` it takes tfp.sts.Sum's default,
+    LogNormal(log(.01 sd), 2)."""
 
     def __init__(self, components, observed_time_series=None, observation_noise_scale_prior: Optional[Prior] = None,
                  prior_level_sd: Optional[float] = None, name='Sum'):
@@ -158,8 +185,7 @@ class Sum:
         self.observed_time_series = observed_time_series
         self._validate_components()
         if observation_noise_scale_prior is None:
-            y = _response_array(observed_time_series)
-            observation_noise_scale_prior = build_bijector(build_inv_gamma_sd_prior(float(np.nanstd(y)) / 2))
+            observation_noise_scale_prior = Prior('LogNormal', {'loc': float('nan'), 'scale': 2.0})
         self.observation_noise_scale_prior = observation_noise_scale_prior
         self.parameters = [Parameter('observation_noise_scale', observation_noise_scale_prior,
                                      'Scale(sd_y) o Softplus')]
@@ -171,14 +197,20 @@ class Sum:
     def _validate_components(self):
         kinds = [type(c) for c in self.components]
         for c in self.components:
-            if not isinstance(c, (LocalLevel, SparseLinearRegression, Seasonal)):
+            if not isinstance(c, (LocalLevel, LocalLinearTrend, SparseLinearRegression, LinearRegression, Seasonal)):
                 raise ValueError(
                     f'Unsupported structural component {type(c).__name__!r}: the B200 kernels implement '
-                    'LocalLevel + SparseLinearRegression + Seasonal only; other tfp.sts components '
-                    'are rejected (no fallback).')
-        if kinds.count(LocalLevel) != 1 or kinds.count(SparseLinearRegression) > 1 or kinds.count(Seasonal) > 1:
-            raise ValueError('Supported model = exactly one LocalLevel, at most one SparseLinearRegression '
-                             'and at most one Seasonal component.')
+                    'LocalLevel | LocalLinearTrend, SparseLinearRegression | LinearRegression and Seasonal '
+                    'only; other tfp.sts components are rejected (no fallback).')
+        if kinds.count(LocalLevel) + kinds.count(LocalLinearTrend) != 1 or \
+                kinds.count(SparseLinearRegression) + kinds.count(LinearRegression) > 1 or kinds.count(Seasonal) > 1:
+            raise ValueError('Supported model = exactly one trend (LocalLevel or LocalLinearTrend), at most one '
+                             'regression (SparseLinearRegression or LinearRegression) and at most one Seasonal '
+                             'component.')
+        order = {LocalLevel: 0, LocalLinearTrend: 0, SparseLinearRegression: 1, LinearRegression: 1, Seasonal: 2}
+        if [order[k] for k in kinds] != sorted(order[k] for k in kinds):
+            raise ValueError('Components must be ordered trend, regression, seasonal (the parameter order of the '
+                             'kernels).')
 
     # ---- lowering to the device layout ----------------------------------------------------------
     def _component(self, cls):
@@ -189,11 +221,32 @@ class Sum:
 
     @property
     def prior_level_sd(self) -> float:
-        pr = self._component(LocalLevel).level_scale_prior
+        ll = self._component(LocalLevel)
+        if ll is None or ll.level_scale_prior.family == 'LogNormal':
+            return 0.01                     # unused: the level scale prior is LogNormal(log(.05 sd), 3)
+        pr = ll.level_scale_prior
         if pr.family != 'SqrtInverseGamma' or abs(pr.params['concentration'] - kLocalLevelPriorSampleSize / 2) > 1e-6:
             raise ValueError('LocalLevel.level_scale_prior must come from build_bijector('
-                             'build_inv_gamma_sd_prior(prior_level_sd)).')
+                             'build_inv_gamma_sd_prior(prior_level_sd)) or be left at its default.')
         return float(np.sqrt(pr.params['scale'] * 2 / kLocalLevelPriorSampleSize))
+
+    @property
+    def flags(self) -> int:
+        """Layout flags of the wider model set (0 = the default model of build_default_model)."""
+        from . import _native as nt
+        f = 0
+        if self._component(LocalLinearTrend) is not None:
+            f |= nt.FLAG_LLT
+        elif self._component(LocalLevel).level_scale_prior.family == 'LogNormal':
+            f |= nt.FLAG_LEVEL_LOGNORMAL
+        if self._component(LinearRegression) is not None:
+            f |= nt.FLAG_DENSE_REG
+        if self.observation_noise_scale_prior.family == 'LogNormal':
+            f |= nt.FLAG_OBS_LOGNORMAL
+        return f
+
+    def _regression(self):
+        return self._component(SparseLinearRegression) or self._component(LinearRegression)
 
     def param_names(self) -> List[str]:
         return [p.name for p in self.parameters]
@@ -213,7 +266,7 @@ class Sum:
         key = (y.tobytes(), int(Tf))
         if self._engine is not None and self._engine[0] == key:
             return self._engine[1]
-        reg, sea = self._component(SparseLinearRegression), self._component(Seasonal)
+        reg, sea = self._regression(), self._component(Seasonal)
         X = None
         if reg is not None:
             X = reg.design_matrix.to_dense()
@@ -223,7 +276,7 @@ class Sum:
         obs_pr = self.observation_noise_scale_prior
         db = DeviceBatch(y[None, :], X, Tf=Tf, nseasons=sea.num_seasons if sea else 1,
                          season_duration=sea.num_steps_per_season if sea else 1,
-                         prior_level_sd=self.prior_level_sd)
+                         prior_level_sd=self.prior_level_sd, flags=self.flags)
         if obs_pr.family == 'SqrtInverseGamma':
             db.set_obs_prior_scale(obs_pr.params['scale'])
         self._engine = (key, db)
@@ -244,7 +297,7 @@ def check_input_model(model, pre_data: pd.DataFrame, post_data: pd.DataFrame) ->
     if not isinstance(model, Sum):
         raise ValueError('Input model must be of type StructuralTimeSeries.')
     for component in model.components:
-        if isinstance(component, SparseLinearRegression):
+        if isinstance(component, (SparseLinearRegression, LinearRegression)):
             expected = (len(pre_data) + len(post_data), len(pre_data.columns) - 1)
             if tuple(component.design_matrix.shape) != expected:
                 raise ValueError(
@@ -288,7 +341,7 @@ def _split_params(model: Sum, theta: torch.Tensor):
 
 
 def _horizon(model: Sum, observed_time_series) -> int:
-    reg = model._component(SparseLinearRegression)
+    reg = model._regression()
     T = len(_response_array(observed_time_series))
     return max(reg.design_matrix.shape[0] - T, 0) if reg is not None else 0
 
