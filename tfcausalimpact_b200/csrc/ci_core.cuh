@@ -15,12 +15,25 @@
 
 namespace ci {
 
-// reciprocal: MUFU.RCP (+1 Newton-free multiply) on device, IEEE divide on host.
+// reciprocal: one MUFU.RCP (rcp.approx, <= 1 ulp) on device, IEEE divide on host.  Arguments on this
+// path are innovation variances / softplus values, far from the denormal and overflow ranges.
 CI_HD float rcp(float x) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(1.0f, x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / x;
+#endif
+}
+
+// log of an innovation variance for the log-likelihood sum: MUFU.LG2 based on device (absolute error
+// ~4e-7 per term, i.e. ~1e-7 relative on the summed log-likelihood), libm on host.
+CI_HD float fast_log(float x) {
+#if defined(__CUDA_ARCH__)
+  return __logf(x);
+#else
+  return logf(x);
 #endif
 }
 

@@ -105,7 +105,7 @@ CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restri
 #pragma unroll
         for (int q = 0; q < S; ++q) tp[(long)q * ldt] = g[q];
         tp[(long)S * ldt] = v;
-        const float term = logf(s) + v * v * is;
+        const float term = fast_log(s) + v * v * is;
         const float yk = term - comp;
         const float tk = acc + yk;
         comp = (tk - acc) - yk;
@@ -327,7 +327,7 @@ struct EffLane {
 #pragma unroll
       for (int q = 0; q < S; ++q) tp[q * TQ] = g[q];
       tp[S * TQ] = v;
-      const float term = logf(s) + v * v * is;
+      const float term = fast_log(s) + v * v * is;
       const float yk = term - comp;
       const float tk = acc + yk;
       comp = (tk - acc) - yk;
