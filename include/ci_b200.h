@@ -47,6 +47,9 @@ typedef struct ci_layout {
   int32_t r;    /* season_duration (model.py:313) */
   int32_t Tpad; /* padded length of the packed design matrix: multiple of 4, >= T + Tf */
   int32_t flags; /* CI_FLAG_*; 0 = the default model of causalimpact/model.py:239-321 */
+  int32_t S2;   /* num_seasons of a SECOND tfp.sts.Seasonal component (0 or 1 = none); custom `model=` only
+                   (notebooks/getting_started.ipynb cell 116: Seasonal(4) + Seasonal(52)); needs S > 1 */
+  int32_t r2;   /* its num_steps_per_season */
 } ci_layout;
 
 /* Wider model set for custom `model=` (causalimpact/main.py:186-252 examples).

@@ -65,6 +65,8 @@ class Layout:
     S: int = 1        # nseasons (1 => no seasonal component)
     r: int = 1        # season_duration
     flags: int = 0    # wider model set (custom `model=`): FLAG_* below
+    S2: int = 1       # num_seasons of a second tfp.sts.Seasonal component (1 => none); custom `model=` only
+    r2: int = 1       # its num_steps_per_season
 
     @property
     def llt(self) -> bool:
@@ -81,7 +83,7 @@ class Layout:
 
     @property
     def d(self) -> int:
-        return self.nt + (self.S - 1 if self.S > 1 else 0)
+        return self.nt + (self.S - 1 if self.S > 1 else 0) + (self.S2 - 1 if self.S2 > 1 else 0)
 
     @property
     def nreg(self) -> int:
@@ -89,7 +91,7 @@ class Layout:
 
     @property
     def P(self) -> int:
-        return 1 + self.nt + self.nreg + (1 if self.S > 1 else 0)
+        return 1 + self.nt + self.nreg + (1 if self.S > 1 else 0) + (1 if self.S2 > 1 else 0)
 
     # offsets into the flat parameter vector (TFP `model.parameters` order)
     @property
@@ -130,11 +132,15 @@ class Layout:
 
     @property
     def i_drift(self) -> int:
+        return self.P - 1 - (1 if self.S2 > 1 else 0)
+
+    @property
+    def i_drift2(self) -> int:
         return self.P - 1
 
     def param_names(self) -> List[str]:
         names = ['observation_noise_scale', 'LocalLevel/_level_scale']
-        if self.flags != 0:
+        if self.flags != 0 or self.S2 > 1:
             raise NotImplementedError('names of the wider model set live in tfcausalimpact_b200.model')
         if self.k > 0:
             names += ['SparseLinearRegression/_global_scale_variance',
@@ -151,6 +157,11 @@ class Layout:
         if self.S <= 1:
             return False
         return (t % (self.S * self.r)) % self.r == self.r - 1
+
+    def is_season_change2(self, t: int) -> bool:
+        if self.S2 <= 1:
+            return False
+        return (t % (self.S2 * self.r2)) % self.r2 == self.r2 - 1
 
 
 @dataclass
@@ -228,13 +239,16 @@ def constrain(u: torch.Tensor, L: Layout, st: SeriesStats, series: torch.Tensor
     if L.S > 1:
         th['Seasonal/_drift_scale'] = sd * softplus(u[:, L.i_drift])
         ldj = ldj + torch.log(sd) + log_sigmoid(u[:, L.i_drift])
+    if L.S2 > 1:
+        th['Seasonal2/_drift_scale'] = sd * softplus(u[:, L.i_drift2])
+        ldj = ldj + torch.log(sd) + log_sigmoid(u[:, L.i_drift2])
     return th, ldj
 
 
 def unconstrain(th: Dict[str, torch.Tensor], L: Layout, st: SeriesStats, series: torch.Tensor
                 ) -> torch.Tensor:
     """Inverse of `constrain` (used to turn constrained draws back into kernel inputs)."""
-    assert L.flags == 0, 'default model only'
+    assert L.flags == 0 and L.S2 <= 1, 'default model only'
 
     def sp_inv(x):
         return x + torch.log(-torch.expm1(-x))
@@ -303,6 +317,8 @@ def log_prior(th: Dict[str, torch.Tensor], L: Layout, st: SeriesStats, series: t
         lp = lp + (-0.5 * LOG_2PI - 0.5 * wn * wn).sum(dim=1)
     if L.S > 1:
         lp = lp + _log_lognormal(th['Seasonal/_drift_scale'], mu01, 3.0)
+    if L.S2 > 1:
+        lp = lp + _log_lognormal(th['Seasonal2/_drift_scale'], mu01, 3.0)
     return lp
 
 
@@ -364,35 +380,51 @@ class DenseSSM:
             F_base[0, 1] = 1.0
             self.Q_base[:, 1, 1] = th['LocalLinearTrend/_slope_scale'] ** 2
             P0[:, 1, 1] = st.sd[series] ** 2
-        F_change = F_base.clone()
-        self.Q_change = self.Q_base.clone()
-        if L.S > 1:
-            S = L.S
+        # seasonal blocks: (offset, S, A, Q block, change predicate)
+        self.blocks = []
+        off = nt
+        for (S, name, pred) in ((L.S, 'Seasonal/_drift_scale', L.is_season_change),
+                                (L.S2, 'Seasonal2/_drift_scale', L.is_season_change2)):
+            if S <= 1:
+                continue
             e2r, r2e = _seasonal_basis(S, dtype)
             perm = np.concatenate([np.arange(1, S), [0]])
             perm_m = torch.as_tensor(np.eye(S)[perm], dtype=dtype)
             A = e2r @ perm_m @ r2e                       # (S-1)x(S-1)
-            F_change[nt:, nt:] = A
             h_eff = torch.zeros(1, S, dtype=dtype)
             h_eff[0, 0] = 1.0
-            H[nt:] = (h_eff @ r2e)[0]
-            drift = th['Seasonal/_drift_scale']
-            self.Q_change[:, nt:, nt:] = ((drift / S) ** 2)[:, None, None] * torch.ones(S - 1, S - 1, dtype=dtype)
+            H[off:off + S - 1] = (h_eff @ r2e)[0]
+            drift = th[name]
+            Qb = ((drift / S) ** 2)[:, None, None] * torch.ones(S - 1, S - 1, dtype=dtype)
             # initial effects prior Normal(y0c, |y0c|+sd) per effect -> residual space
             mean_eff = st.y0c[series][:, None] * torch.ones(1, S, dtype=dtype)
-            m0[:, nt:] = mean_eff @ e2r.T
+            m0[:, off:off + S - 1] = mean_eff @ e2r.T
             cov_res = e2r @ e2r.T
-            P0[:, nt:, nt:] = (s0 * s0)[:, None, None] * cov_res
+            P0[:, off:off + S - 1, off:off + S - 1] = (s0 * s0)[:, None, None] * cov_res
+            self.blocks.append((off, S, A, Qb, pred))
+            off += S - 1
         self.H = H
-        self.F_change = F_change
         self.F_id = F_base
         self.m0, self.P0 = m0, P0
+        self._cache = {}
+
+    def _mats(self, t: int):
+        key = tuple(bool(pred(t)) for (_, _, _, _, pred) in self.blocks)
+        if key not in self._cache:
+            F = self.F_id.clone()
+            Q = self.Q_base.clone()
+            for on, (off, S, A, Qb, _) in zip(key, self.blocks):
+                if on:
+                    F[off:off + S - 1, off:off + S - 1] = A
+                    Q[:, off:off + S - 1, off:off + S - 1] = Qb
+            self._cache[key] = (F, Q)
+        return self._cache[key]
 
     def F(self, t: int) -> torch.Tensor:
-        return self.F_change if (self.L.S > 1 and self.L.is_season_change(t)) else self.F_id
+        return self._mats(t)[0]
 
     def Q(self, t: int) -> torch.Tensor:
-        return self.Q_change if (self.L.S > 1 and self.L.is_season_change(t)) else self.Q_base
+        return self._mats(t)[1]
 
 
 def kalman_filter(ssm: DenseSSM, resid: torch.Tensor, t0: int = 0):

@@ -40,3 +40,10 @@ def test_argument_validation_without_gpu():
     assert lib.ci_eval_workspace_bytes(ctypes.byref(huge_s)) > 0
     assert lib.ci_fstate_floats(ctypes.byref(nt.make_layout(1, 1, 10, 2, 0, 7, 1))) == 7 + 7 * 8
     assert lib.ci_fstate_floats(ctypes.byref(nt.make_layout(1, 1, 10, 2, 0, 52, 1))) == 53 + 2 * 53 * 53
+    # second Seasonal component (custom `model=`): latent = level + slope + 4 + 52 effects, 2 drift scales
+    two = nt.make_layout(1, 1, 10, 2, 3, 4, 1, flags=nt.FLAG_LLT | nt.FLAG_DENSE_REG, S2=52, r2=1)
+    assert lib.ci_num_params_layout(ctypes.byref(two)) == 1 + 2 + 3 + 2 == nt.num_params(3, 4, two.flags, 52)
+    assert lib.ci_fstate_floats(ctypes.byref(two)) == 58 + 2 * 58 * 58
+    second_without_first = nt.make_layout(1, 1, 10, 2, 0, 1, 1, S2=4, r2=1)
+    assert lib.ci_series_stats(ctypes.byref(second_without_first), None, ctypes.c_float(0.01), None, None) == -1
+    assert b'second seasonal' in lib.ci_last_error_string()

@@ -116,3 +116,41 @@ def test_wider_model_set_logp_grad_matches_oracle(flags, S, r, k, T, nan_frac, N
     ud = torch.as_tensor(u).cuda()
     th = db.constrain(ud)
     np.testing.assert_allclose(db.unconstrain(th).cpu().numpy(), u, rtol=2e-4, atol=2e-4)
+
+
+# two Seasonal components (custom `model=`; notebooks/getting_started.ipynb cell 116: Month(4) + Year(52))
+TWO_SEASONAL_CASES = [
+    # flags, S, r, S2, r2, k, T, nan_frac, N, G
+    (O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 4, 1, 52, 1, 3, 120, 0.0, 2, 2),   # the notebook's model
+    (0, 7, 1, 4, 3, 2, 60, 0.1, 2, 2),                   # default priors + a second seasonal with duration 3
+    (O.FLAG_LLT | O.FLAG_OBS_LOGNORMAL, 3, 2, 5, 1, 0, 50, 0.05, 1, 3),
+    (O.FLAG_OBS_LOGNORMAL | O.FLAG_LEVEL_LOGNORMAL, 12, 1, 30, 2, 1, 90, 0.0, 1, 2),
+]
+
+
+@pytest.mark.parametrize('flags,S,r,S2,r2,k,T,nan_frac,N,G', TWO_SEASONAL_CASES)
+def test_two_seasonal_components_logp_grad_matches_oracle(flags, S, r, S2, r2, k, T, nan_frac, N, G):
+    from tfcausalimpact_b200.engine import DeviceBatch
+    Tf = 7
+    L = O.Layout(T, Tf, k, S, r, flags, S2, r2)
+    y, _, X = synth_problem(N, T, Tf, k, S, r, seed=S * 10 + S2 + k + flags, nan_frac=nan_frac)
+    prob = O.Problem.build(y, X, L, dtype=torch.float64)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S, season_duration=r, flags=flags,
+                     nseasons2=S2, season_duration2=r2)
+    assert db.P == L.P
+    rng = np.random.default_rng(2)
+    B = N * G
+    u = (rng.normal(size=(L.P, B)) * 0.6).astype(np.float32)
+    u[0] -= 1.0
+    u[1:1 + L.nt] -= 2.0
+    lp, g = db.logp_grad(torch.as_tensor(u).cuda())
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    series = torch.arange(B) // G
+    lpo, go = O.target_log_prob_and_grad(prob, torch.tensor(u.T.astype(np.float64)), series)
+    lpo, go = lpo.numpy(), go.numpy().T
+    np.testing.assert_allclose(lp, lpo, rtol=1e-4)
+    gmax = np.abs(go).max(axis=0, keepdims=True)
+    assert np.all(np.abs(g - go) <= 1e-4 * np.abs(go) + 1e-5 * gmax)
+    ud = torch.as_tensor(u).cuda()
+    th = db.constrain(ud)
+    np.testing.assert_allclose(db.unconstrain(th).cpu().numpy(), u, rtol=2e-4, atol=2e-4)

@@ -225,3 +225,48 @@ def test_custom_model_local_linear_trend_and_linear_regression():
     assert np.isfinite(ci2.summary_data.values).all()
     with pytest.raises(ValueError):
         M.Sum([M.LocalLevel(), M.LocalLinearTrend()], observed_time_series=obs)
+
+
+def test_custom_model_two_seasonal_components_notebook_cell_116():
+    """notebooks/getting_started.ipynb cells 116-118: LocalLinearTrend + LinearRegression + Seasonal(4, 'Month')
+    + Seasonal(52, 'Year') on weekly data, passed as `model=` (the notebook's own data came from a web
+    download, so the same model runs on a synthetic weekly panel of that shape: 146 + 6 weeks, 7 covariates)."""
+    from tfcausalimpact_b200 import model as M
+    from tfcausalimpact_b200.misc import standardize
+    rng = np.random.default_rng(116)
+    n, npre = 152, 146
+    idx = pd.date_range('2018-01-03', periods=n, freq='7D')
+    Xc = np.cumsum(rng.normal(scale=0.3, size=(n, 7)), axis=0) + 10
+    month = np.array([0.6, -0.2, -0.5, 0.1])[np.arange(n) % 4]
+    year = 1.5 * np.sin(2 * np.pi * np.arange(n) / 52.0)
+    y = 20 + 0.02 * np.arange(n) + 0.8 * Xc[:, 0] - 0.5 * Xc[:, 3] + month + year + rng.normal(scale=0.3, size=n)
+    y[npre:] += 2.0
+    data = pd.DataFrame(np.column_stack([y, Xc]), index=idx,
+                        columns=['BTC-USD', 'TWTR', 'GOOGL', 'AAPL', 'MSFT', 'AMZN', 'FB', 'GOLD'])
+    pre_period = [str(idx[0].date()), str(idx[npre - 1].date())]
+    post_period = [str(idx[npre].date()), str(idx[-1].date())]
+    normed_data, mu_sig = standardize(data)
+    obs_data = normed_data['BTC-USD'].loc[:pre_period[1]].astype(np.float32)
+    design_matrix = pd.concat([normed_data.loc[pre_period[0]: pre_period[1]],
+                               normed_data.loc[post_period[0]: post_period[1]]]).astype(np.float32).iloc[:, 1:]
+    linear_level = M.LocalLinearTrend(observed_time_series=obs_data)
+    linear_reg = M.LinearRegression(design_matrix=design_matrix)
+    month_season = M.Seasonal(num_seasons=4, num_steps_per_season=1, observed_time_series=obs_data, name='Month')
+    year_season = M.Seasonal(num_seasons=52, observed_time_series=obs_data, name='Year')
+    model = M.Sum([linear_level, linear_reg, month_season, year_season], observed_time_series=obs_data)
+    assert model.param_names() == ['observation_noise_scale', 'LocalLinearTrend/_level_scale',
+                                   'LocalLinearTrend/_slope_scale', 'LinearRegression/_weights',
+                                   'Month/_drift_scale', 'Year/_drift_scale']
+    np.random.seed(116)
+    ci = _ci(data, pre_period, post_period, model=model)
+    assert list(ci.model_samples.keys()) == model.param_names()
+    assert tuple(ci.model_samples['LinearRegression/_weights'].shape) == (100, 7)
+    s = ci.summary_data
+    assert np.isfinite(s.values).all()
+    assert abs(s.loc['abs_effect', 'average'] - 2.0) < 1.0
+    assert s.loc['abs_effect_lower', 'average'] < s.loc['abs_effect', 'average'] < s.loc['abs_effect_upper', 'average']
+    with pytest.raises(ValueError):
+        M.Sum([linear_level, month_season, year_season, M.Seasonal(num_seasons=3, name='Third')],
+              observed_time_series=obs_data)
+    with pytest.raises(ValueError):
+        M.Sum([linear_level, M.Seasonal(num_seasons=4), M.Seasonal(num_seasons=52)], observed_time_series=obs_data)

@@ -204,3 +204,41 @@ def test_wider_model_set_filter_and_forecast(flags, N, G, T, Tf, k, S, r, nan_fr
     mix_var = (vars_o + means_o ** 2).mean(axis=1) - mix_mean ** 2
     assert np.all(np.abs(s.mean(axis=1) - mix_mean) < 5 * np.sqrt(mix_var / nsamp))
     assert np.all(np.abs(s.var(axis=1) / mix_var - 1.0) < 0.25)
+
+
+TWO_SEASONAL = [(O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 1, 3, 120, 12, 3, 4, 1, 52, 1, 0.0),
+                (0, 2, 2, 60, 14, 2, 7, 1, 4, 3, 0.1),
+                (O.FLAG_LLT | O.FLAG_OBS_LOGNORMAL, 2, 2, 50, 11, 0, 3, 2, 5, 1, 0.0)]
+
+
+@pytest.mark.parametrize('flags,N,G,T,Tf,k,S,r,S2,r2,nan_frac', TWO_SEASONAL)
+def test_two_seasonal_components_filter_and_forecast(flags, N, G, T, Tf, k, S, r, S2, r2, nan_frac):
+    from tfcausalimpact_b200.engine import DeviceBatch
+    L = O.Layout(T, Tf, k, S, r, flags, S2, r2)
+    y, _, X = synth_problem(N, T, Tf, k, S, r, seed=35, nan_frac=nan_frac)
+    prob = O.Problem.build(y, X, L, dtype=torch.float64)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S, season_duration=r, flags=flags,
+                     nseasons2=S2, season_duration2=r2)
+    B = N * G
+    rng = np.random.default_rng(8)
+    u = (rng.normal(size=(L.P, B)) * 0.4).astype(np.float32)
+    u[0] -= 1.0
+    u[1:1 + L.nt] -= 2.0
+    ud = torch.as_tensor(u).cuda()
+    pm, pv, fs = db.filter_predict(ud)
+    series = torch.arange(B) // G
+    uo = torch.as_tensor(u.T.astype(np.float64))
+    mean_o, var_o, _, _, _, _ = O.one_step_predictive(prob, uo, series)
+    np.testing.assert_allclose(pm.cpu().numpy().T, mean_o.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(pv.cpu().numpy().T, var_o.numpy(), rtol=1e-4)
+    nsamp = 4000
+    sims, mean = db.forecast_sample(ud, fs, nsamp, seed=5)
+    means_o, vars_o = O.forecast_moments(prob, uo, series)
+    means_o = means_o.numpy().reshape(N, G, Tf)
+    vars_o = vars_o.numpy().reshape(N, G, Tf)
+    np.testing.assert_allclose(mean.cpu().numpy(), means_o.mean(axis=1), rtol=1e-4, atol=1e-4)
+    s = sims.cpu().numpy().astype(np.float64)
+    mix_mean = means_o.mean(axis=1)
+    mix_var = (vars_o + means_o ** 2).mean(axis=1) - mix_mean ** 2
+    assert np.all(np.abs(s.mean(axis=1) - mix_mean) < 5 * np.sqrt(mix_var / nsamp))
+    assert np.all(np.abs(s.var(axis=1) / mix_var - 1.0) < 0.25)

@@ -18,7 +18,8 @@ class NativeError(RuntimeError):
 
 
 class CiLayout(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ('N', 'G', 'T', 'Tf', 'k', 'S', 'r', 'Tpad', 'flags')]
+    # S2 / r2: second Seasonal component of a custom model (0 = none); see include/ci_b200.h
+    _fields_ = [(n, ctypes.c_int32) for n in ('N', 'G', 'T', 'Tf', 'k', 'S', 'r', 'Tpad', 'flags', 'S2', 'r2')]
 
 
 class CiData(ctypes.Structure):
@@ -67,13 +68,13 @@ def stream_ptr():
 FLAG_DENSE_REG, FLAG_LLT, FLAG_OBS_LOGNORMAL, FLAG_LEVEL_LOGNORMAL = 1, 2, 4, 8
 
 
-def make_layout(N, G, T, Tf, k, S=1, r=1, Tpad=None, flags=0):
+def make_layout(N, G, T, Tf, k, S=1, r=1, Tpad=None, flags=0, S2=0, r2=0):
     if Tpad is None:
         Tpad = (T + Tf + 3) // 4 * 4
-    return CiLayout(N, G, T, Tf, k, S, r, Tpad, flags)
+    return CiLayout(N, G, T, Tf, k, S, r, Tpad, flags, S2, r2)
 
 
-def num_params(k, S, flags=0):
+def num_params(k, S, flags=0, S2=0):
     trend = 2 if flags & FLAG_LLT else 1
     reg = 0 if k == 0 else (k if flags & FLAG_DENSE_REG else 2 + 3 * k)
-    return 1 + trend + reg + (1 if S > 1 else 0)
+    return 1 + trend + reg + (1 if S > 1 else 0) + (1 if S2 > 1 else 0)

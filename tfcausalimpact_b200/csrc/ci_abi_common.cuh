@@ -37,15 +37,20 @@ inline int check_layout(const ci_layout* L) {
     return fail(CI_ERR_INVALID_ARGUMENT, "layout has a non-positive dimension");
   if (L->S == 1 && L->r != 1) return fail(CI_ERR_INVALID_ARGUMENT, "season_duration > 1 needs nseasons > 1");
   if (L->flags & ~15) return fail(CI_ERR_INVALID_ARGUMENT, "unknown layout flags");
+  if (L->S2 < 0 || L->r2 < 0) return fail(CI_ERR_INVALID_ARGUMENT, "layout has a negative second-seasonal dimension");
+  if (L->S2 > 1 && (L->S <= 1 || L->r2 < 1))
+    return fail(CI_ERR_INVALID_ARGUMENT, "a second seasonal component needs nseasons > 1 and season_duration2 >= 1");
   if (L->Tpad % 4 != 0 || L->Tpad < L->T + L->Tf)
     return fail(CI_ERR_INVALID_ARGUMENT, "Tpad must be a multiple of 4 and >= T + Tf");
   return CI_OK;
 }
 
 // default model on the register-resident kernels; everything else on the warp-per-lane path
-inline bool ci_reg_path(const ci_layout* L) { return L->flags == 0 && ci_reg_set(L->S); }
+inline bool ci_two_seasonal(const ci_layout* L) { return L->S2 > 1; }
+inline bool ci_gen_params(const ci_layout* L) { return L->flags != 0 || L->S2 > 1; }
+inline bool ci_reg_path(const ci_layout* L) { return !ci_gen_params(L) && ci_reg_set(L->S); }
 inline int layout_num_params(const ci_layout* L) {
-  return L->flags == 0 ? num_params(L->k, L->S) : num_params_gen(L->k, L->S, L->flags);
+  return ci_gen_params(L) ? num_params_gen(L->k, L->S, L->flags, L->S2) : num_params(L->k, L->S);
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -15,6 +15,11 @@
 //                 predicted state + guarded Cholesky                    replaces: as ci_predict.cu K6
 //   k_forecast_mean_big / k_forecast_sample_big   forecast mean path and joint trajectories   (K7)
 // Forecast-state layout of this path: lane-contiguous [B][D + 2 D^2] = m, P (full), chol(P) (full).
+//
+// A SECOND seasonal component (ci_layout.S2 > 1; tfp.sts.Sum([..., Seasonal(S), Seasonal(S2)]), the
+// notebook's Month + Year model) appends its S2 effects to the latent vector: H_t gains a third one
+// (e_{so2 + c2}), Q_t a second rank-1 drift block.  Kernels are templated on TWO so the single-seasonal
+// instantiations carry none of it.
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
 
@@ -28,27 +33,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// latent layout: [level | slope (LocalLinearTrend only) | e_0 .. e_{S-1} (S > 1 only)]
+// latent layout: [level | slope (LocalLinearTrend only) | e_0 .. e_{S-1} (S > 1 only) | e'_0 .. e'_{S2-1} (S2 > 1 only)]
 __host__ __device__ __forceinline__ int big_nt(const ci_layout& L) { return (L.flags & CI_FLAG_LLT) ? 2 : 1; }
-__host__ __device__ __forceinline__ int big_D(const ci_layout& L) { return big_nt(L) + (L.S > 1 ? L.S : 0); }
+__host__ __device__ __forceinline__ int big_so2(const ci_layout& L) { return big_nt(L) + (L.S > 1 ? L.S : 0); }
+__host__ __device__ __forceinline__ int big_D(const ci_layout& L) { return big_so2(L) + (L.S2 > 1 ? L.S2 : 0); }
+__host__ __device__ __forceinline__ bool big_gen(const ci_layout& L) { return L.flags != 0 || L.S2 > 1; }
 
 __device__ __forceinline__ int season_of(int t, int S, int r) { return (t / r) % S; }
 __device__ __forceinline__ bool season_change(int t, int S, int r) { return S > 1 && (t % r) == r - 1; }
 // drift-direction weight of state index i (0 = level) when season c was just observed
 // (so = index of the first seasonal effect)
 __device__ __forceinline__ float drift_w(int i, int c, int S, int so) {
-  return i < so ? 0.f : (i == so + c ? (float)(1 - S) : 1.f);
+  return (i < so || i >= so + S) ? 0.f : (i == so + c ? (float)(1 - S) : 1.f);
 }
 
-__device__ void big_init(float* P, float* m, int D, int S, int so, float m0, float p0, float sd, int lane) {
+__device__ void big_init(float* P, float* m, int D, int S, int so, int S2, float m0, float p0, float sd, int lane) {
   const float off = S > 1 ? -p0 / (float)S : 0.f;
+  const float off2 = S2 > 1 ? -p0 / (float)S2 : 0.f;
+  const int so2 = so + (S > 1 ? S : 0);
   for (int i = 0; i < D; ++i)
     for (int j = lane; j < D; j += 32) {
       float v = 0.f;
       if (i < so || j < so) {
         if (i == j) v = (i == 0) ? p0 : sd * sd;      // level: (|y0c| + sd)^2 ; slope: sd^2
-      } else {
+      } else if (i < so2 && j < so2) {
         v = (i == j) ? p0 + off : off;
+      } else if (i >= so2 && j >= so2) {
+        v = (i == j) ? p0 + off2 : off2;
       }
       P[i * D + j] = v;
     }
@@ -85,27 +96,47 @@ struct Cols {
 
 // One filter step on the shared-memory state.  Returns false when the step is masked.
 // Emits g (shared) and s, v; the time update (P += Q_t) is fused into the same row sweep.
-template <int NC, int RB>
-__device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int so, int c, bool change, float resid,
-                                         float R, float ql, float qs, float qd, float& s, float& v, float& is, int lane) {
+// season bookkeeping of one step (both components)
+struct BigSeason {
+  int c, J, c2, J2;        // season index / latent index of the observed effect (J2 = 0 when !TWO)
+  bool change, change2;
+};
+template <bool TWO>
+__device__ __forceinline__ BigSeason big_season(const ci_layout& L, int so, int so2, int t) {
+  BigSeason z;
+  z.c = L.S > 1 ? season_of(t, L.S, L.r) : 0;
+  z.J = L.S > 1 ? so + z.c : 0;
+  z.change = season_change(t, L.S, L.r);
+  z.c2 = TWO ? season_of(t, L.S2, L.r2) : 0;
+  z.J2 = TWO ? so2 + z.c2 : 0;
+  z.change2 = TWO && season_change(t, L.S2, L.r2);
+  return z;
+}
+
+template <int NC, int RB, bool TWO>
+__device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int so,
+                                         int S2, int so2, const BigSeason z, float resid, float R, float ql, float qs,
+                                         float qd, float qd2, float& s, float& v, float& is, int lane) {
   const Cols<NC> cl(lane, D);
-  const int J = S > 1 ? so + c : 0;
+  const int c = z.c, J = z.J, J2 = z.J2;
   const bool obs = (resid == resid);
-  float gj[NC], wj[NC];
+  float gj[NC], wj[NC], w2j[NC];
 #pragma unroll
   for (int q = 0; q < NC; ++q) {
-    gj[q] = cl.ok[q] ? P[cl.j[q] * D] + (S > 1 ? P[cl.j[q] * D + J] : 0.f) : 0.f;
+    gj[q] = cl.ok[q] ? P[cl.j[q] * D] + (S > 1 ? P[cl.j[q] * D + J] : 0.f) + (TWO ? P[cl.j[q] * D + J2] : 0.f) : 0.f;
     wj[q] = drift_w(cl.j[q], c, S, so);
+    w2j[q] = TWO ? drift_w(cl.j[q], z.c2, S2, so2) : 0.f;
     if (cl.ok[q]) g[cl.j[q]] = gj[q];
   }
   __syncwarp();
-  s = g[0] + (S > 1 ? g[J] : 0.f) + R;
-  v = resid - m[0] - (S > 1 ? m[J] : 0.f);
+  s = g[0] + (S > 1 ? g[J] : 0.f) + (TWO ? g[J2] : 0.f) + R;
+  v = resid - m[0] - (S > 1 ? m[J] : 0.f) - (TWO ? m[J2] : 0.f);
   is = rcp(s);
   const float vis = v * is;
   __syncwarp();
   const float nis = obs ? -is : 0.f;
-  const float qq = change ? qd : 0.f;
+  const float qq = z.change ? qd : 0.f;
+  const float qq2 = z.change2 ? qd2 : 0.f;
   if (obs) {
 #pragma unroll
     for (int q = 0; q < NC; ++q)
@@ -115,12 +146,13 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
   // SM busy): all loads of a batch are issued before its stores, so shared-memory latency is
   // paid once per batch instead of once per row (the compiler cannot reorder a load of P past a store to P)
   for (int i0 = 0; i0 < D; i0 += RB) {
-    float p[RB][NC], nki[RB], qi[RB];
+    float p[RB][NC], nki[RB], qi[RB], q2i[RB];
 #pragma unroll
     for (int e = 0; e < RB; ++e) {
       const int i = i0 + e < D ? i0 + e : D - 1;
       nki[e] = g[i] * nis;
       qi[e] = qq * drift_w(i, c, S, so);
+      q2i[e] = TWO ? qq2 * drift_w(i, z.c2, S2, so2) : 0.f;
 #pragma unroll
       for (int q = 0; q < NC; ++q) p[e][q] = P[i * D + cl.j[q]];
     }
@@ -129,7 +161,11 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
       if (i0 + e < D) {
 #pragma unroll
         for (int q = 0; q < NC; ++q)
-          if (cl.ok[q]) P[(i0 + e) * D + cl.j[q]] = fmaf(qi[e], wj[q], fmaf(nki[e], gj[q], p[e][q]));
+          if (cl.ok[q]) {
+            float nv = fmaf(qi[e], wj[q], fmaf(nki[e], gj[q], p[e][q]));
+            if (TWO) nv = fmaf(q2i[e], w2j[q], nv);
+            P[(i0 + e) * D + cl.j[q]] = nv;
+          }
       }
     }
   }
@@ -153,12 +189,12 @@ __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restric
   return obs;
 }
 
-template <int NC>
+template <int NC, bool TWO>
 __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
            float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
-  const int S = L.S, so = big_nt(L), D = big_D(L), k = L.k, T = L.T, r = L.r;
+  const int S = L.S, so = big_nt(L), so2 = big_so2(L), S2 = TWO ? L.S2 : 1, D = big_D(L), k = L.k, T = L.T;
   const long B = (long)L.N * L.G;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long b = (long)blockIdx.x * BIG_WARPS + w;
@@ -174,26 +210,26 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   float* beta = gb + D;
   float* scal = beta + (k > 0 ? k : 1);
   if (lane == 0) {
-    if (L.flags == 0) {
+    if (!big_gen(L)) {
       const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
-      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = 0.f;
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = 0.f; scal[5] = 0.f;
     } else {
-      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1);
-      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = ls.qs;
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, L.S2);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = ls.qs; scal[5] = ls.qd2;
     }
   }
   __syncwarp();
-  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3], qs = scal[4];
-  big_init(P, m, D, S, so, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
+  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3], qs = scal[4], qd2 = scal[5];
+  big_init(P, m, D, S, so, S2, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
   const Cols<NC> cl(lane, D);
   float* tp = tape + b * (long)T * (D + 1);
   float acc = 0.f, comp = 0.f;
   int nobs = 0;
   for (int t = 0; t < T; ++t) {
-    const int c = S > 1 ? season_of(t, S, r) : 0;
+    const BigSeason z = big_season<TWO>(L, so, so2, t);
     const float resid = big_resid(XY, L, n, t, beta, lane);
     float s, v, is;
-    const bool obs = big_step<NC, 4>(P, m, g, D, S, so, c, season_change(t, S, r), resid, R, ql, qs, qd, s, v, is, lane);
+    const bool obs = big_step<NC, 4, TWO>(P, m, g, D, S, so, S2, so2, z, resid, R, ql, qs, qd, qd2, s, v, is, lane);
     float* te = tp + (long)t * (D + 1);
 #pragma unroll
     for (int q = 0; q < NC; ++q)
@@ -216,7 +252,7 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   for (int j = lane; j < D; j += 32) mb[j] = 0.f;
   for (int j = lane; j < k; j += 32) beta[j] = 0.f;   // becomes beta_bar
   __syncwarp();
-  float Rb = 0.f, qlb = 0.f, qsb = 0.f, qdb = 0.f;
+  float Rb = 0.f, qlb = 0.f, qsb = 0.f, qdb = 0.f, qd2b = 0.f;
   const int stride = (k + 1) * CI_TC;
   // software-pipelined tape reads: the entry of step t-1 is requested before step t is processed
   float cur_g[NC], cur_v, nxt_g[NC], nxt_v = 0.f;
@@ -230,8 +266,8 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     }
   }
   for (int t = T - 1; t >= 0; --t) {
-    const int c = S > 1 ? season_of(t, S, r) : 0;
-    const int J = S > 1 ? so + c : 0;
+    const BigSeason z = big_season<TWO>(L, so, so2, t);
+    const int c = z.c, J = z.J, J2 = z.J2;
     if (t > 0) {
       const float* tn = tp + (long)(t - 1) * (D + 1);
       nxt_v = tn[D];
@@ -240,12 +276,13 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     }
     const float v = cur_v;
     const bool obs = (v == v);
-    const bool change = season_change(t, S, r);
-    float gj[NC], wj[NC];
+    const bool change = z.change, change2 = z.change2;
+    float gj[NC], wj[NC], w2j[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
       gj[q] = obs ? cur_g[q] : 0.f;
       wj[q] = cl.ok[q] ? drift_w(cl.j[q], c, S, so) : 0.f;
+      w2j[q] = (TWO && cl.ok[q]) ? drift_w(cl.j[q], z.c2, S2, so2) : 0.f;
       if (cl.ok[q]) g[cl.j[q]] = gj[q];
     }
     qlb += Pb[0];
@@ -262,20 +299,22 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
       if (lane == 0) mb[1] += mb[0];
     }
     __syncwarp();
-    // one sweep over Pbar gives both the adjoint of the drift term (w^T Pbar w) and Pg = Pbar g
-    float col[NC], nac[NC];
+    // one sweep over Pbar gives the adjoints of the drift terms (w^T Pbar w) and Pg = Pbar g
+    float col[NC], nac[NC], nac2[NC];
 #pragma unroll
-    for (int q = 0; q < NC; ++q) col[q] = nac[q] = 0.f;
-    if (obs || change) {
+    for (int q = 0; q < NC; ++q) col[q] = nac[q] = nac2[q] = 0.f;
+    if (obs || change || change2) {
 #pragma unroll 4
       for (int i = 0; i < D; ++i) {
         const float gi = g[i];
         const float wi = drift_w(i, c, S, so);
+        const float w2i = TWO ? drift_w(i, z.c2, S2, so2) : 0.f;
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
           const float pb = Pb[i * D + cl.j[q]];
           col[q] = fmaf(pb, gi, col[q]);
           nac[q] = fmaf(pb, wi, nac[q]);
+          if (TWO) nac2[q] = fmaf(pb, w2i, nac2[q]);
         }
       }
     }
@@ -285,8 +324,14 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
       for (int q = 0; q < NC; ++q) part = fmaf(wj[q], nac[q], part);
       qdb += warp_sum(part);
     }
+    if (TWO && change2) {
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) part = fmaf(w2j[q], nac2[q], part);
+      qd2b += warp_sum(part);
+    }
     if (obs) {
-      const float s = g[0] + (S > 1 ? g[J] : 0.f) + R;
+      const float s = g[0] + (S > 1 ? g[J] : 0.f) + (TWO ? g[J2] : 0.f) + R;
       const float is = rcp(s);
       float pa = 0.f, pg = 0.f;
 #pragma unroll
@@ -303,12 +348,13 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
       Rb += sbar;
       float gbj[NC];
 #pragma unroll
-      for (int q = 0; q < NC; ++q)
-        gbj[q] = cl.ok[q] ? fmaf(mb[cl.j[q]], vis,
-                                 fmaf(-2.f * is, col[q], (cl.j[q] == 0 || (S > 1 && cl.j[q] == J)) ? sbar : 0.f))
-                          : 0.f;
+      for (int q = 0; q < NC; ++q) {
+        const bool inH = cl.j[q] == 0 || (S > 1 && cl.j[q] == J) || (TWO && cl.j[q] == J2);
+        gbj[q] = cl.ok[q] ? fmaf(mb[cl.j[q]], vis, fmaf(-2.f * is, col[q], inH ? sbar : 0.f)) : 0.f;
+      }
       __syncwarp();
-      // Pbar += sym(gb H^T): column/row 0, then column/row J (two phases: (0,J) is touched by both)
+      // Pbar += sym(gb H^T): column/row 0, then column/row J (then J2): separate phases because the
+      // crossing entries (0,J), (0,J2), (J,J2) are touched by two of them
 #pragma unroll
       for (int q = 0; q < NC; ++q) {
         if (cl.ok[q]) {
@@ -328,9 +374,21 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
           }
         }
       }
+      if (TWO) {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          if (cl.ok[q]) {
+            const float h = 0.5f * gbj[q];
+            Pb[cl.j[q] * D + J2] += h;
+            Pb[J2 * D + cl.j[q]] += h;
+          }
+        }
+      }
       if (lane == 0) {
         mb[0] -= vb;
         if (S > 1) mb[J] -= vb;
+        if (TWO) mb[J2] -= vb;
       }
       // beta_bar_j -= rbar X_tj
       const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
@@ -343,19 +401,19 @@ k_eval_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   }
   (void)gb;
   if (lane == 0) {
-    if (L.flags == 0) params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
-    else params_backward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, Rb, qlb, qsb, qdb, grad + b);
+    if (!big_gen(L)) params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
+    else params_backward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, Rb, qlb, qsb, qdb, grad + b, L.S2, qd2b);
     logp[b] = ll + lp0;
   }
 }
 
 // Forward filter per draw lane: one-step predictive mean/variance + forecast state.
-template <int NC>
+template <int NC, bool TWO>
 __global__ void __launch_bounds__(BIG_WARPS * 32)
 k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
              float* __restrict__ pred_mean, float* __restrict__ pred_var, float* __restrict__ fstate) {
   extern __shared__ __align__(16) float smem[];
-  const int S = L.S, so = big_nt(L), D = big_D(L), k = L.k, T = L.T, r = L.r;
+  const int S = L.S, so = big_nt(L), so2 = big_so2(L), S2 = TWO ? L.S2 : 1, D = big_D(L), k = L.k, T = L.T;
   const long B = (long)L.N * L.G;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long b = (long)blockIdx.x * BIG_WARPS + w;
@@ -369,20 +427,20 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
   float* beta = g + 3 * D;
   float* scal = beta + (k > 0 ? k : 1);
   if (lane == 0) {
-    if (L.flags == 0) {
+    if (!big_gen(L)) {
       const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
-      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = 0.f;
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = 0.f; scal[5] = 0.f;
     } else {
-      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1);
-      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = ls.qs;
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, L.S2);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = ls.qs; scal[5] = ls.qd2;
     }
   }
   __syncwarp();
-  const float R = scal[0], ql = scal[1], qd = scal[2], qs = scal[4];
+  const float R = scal[0], ql = scal[1], qd = scal[2], qs = scal[4], qd2 = scal[5];
   const float mean = sconst[SC_MEAN * L.N + n];
-  big_init(P, m, D, S, so, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
+  big_init(P, m, D, S, so, S2, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
   for (int t = 0; t < T; ++t) {
-    const int c = S > 1 ? season_of(t, S, r) : 0;
+    const BigSeason z = big_season<TWO>(L, so, so2, t);
     const float resid = big_resid(XY, L, n, t, beta, lane);      // (y - mean) - X beta, NaN if masked
     // offset_t = mean + X_t beta = y_t - resid when observed; recompute it for masked steps
     const int stride = (k + 1) * CI_TC;
@@ -391,8 +449,8 @@ k_filter_big(ci_layout L, const float* __restrict__ XY, const float* __restrict_
     for (int j = lane; j < k; j += 32) xb = fmaf(beta[j], __ldg(xp + j * CI_TC), xb);
     xb = warp_sum(xb);
     float s, v, is;
-    const float hm = m[0] + (S > 1 ? m[so + c] : 0.f);
-    big_step<NC, 8>(P, m, g, D, S, so, c, season_change(t, S, r), resid, R, ql, qs, qd, s, v, is, lane);
+    const float hm = m[0] + (S > 1 ? m[z.J] : 0.f) + (TWO ? m[z.J2] : 0.f);
+    big_step<NC, 8, TWO>(P, m, g, D, S, so, S2, so2, z, resid, R, ql, qs, qd, qd2, s, v, is, lane);
     if (lane == 0) {
       pred_mean[(long)t * B + b] = hm + mean + xb;
       pred_var[(long)t * B + b] = s;
@@ -443,7 +501,8 @@ __global__ void k_forecast_mean_big(ci_layout L, const float* __restrict__ fstat
   const int t = (int)(idx / B);
   const float* fs = fstate + b * (long)(D + 2 * D * D);
   const int c = S > 1 ? season_of(L.T + t, S, L.r) : 0;
-  pm[idx] = fs[0] + (so == 2 ? (float)t * fs[1] : 0.f) + (S > 1 ? fs[so + c] : 0.f) + off[idx];
+  const float second = L.S2 > 1 ? fs[big_so2(L) + season_of(L.T + t, L.S2, L.r2)] : 0.f;
+  pm[idx] = fs[0] + (so == 2 ? (float)t * fs[1] : 0.f) + (S > 1 ? fs[so + c] : 0.f) + second + off[idx];
 }
 
 #define CI_BIG_MAXD 96
@@ -461,6 +520,8 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
   const long b = (long)n * L.G + pick_draw_big((uint32_t)si, 1u, L.G, seed);
   const float sobs = sqrtf(scal[0 * B + b]), sl = sqrtf(scal[1 * B + b]), sdr = sqrtf(scal[2 * B + b]);
   const float sslope = so == 2 ? sqrtf(scal[4 * B + b]) : 0.f;
+  const int S2 = L.S2 > 1 ? L.S2 : 1, so2 = big_so2(L);
+  const float sdr2 = S2 > 1 ? sqrtf(scal[5 * B + b]) : 0.f;
   const float mu = mu_sig ? mu_sig[n] : 0.f, sg = mu_sig ? mu_sig[L.N + n] : 1.f;
   const float* fs = fstate + b * (long)(D + 2 * D * D);
   const float* Lc = fs + D + D * D;
@@ -482,7 +543,8 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
       const int t = t0 + q;
       const int c = S > 1 ? season_of(L.T + t, S, r) : 0;
       const f32x4 e = philox_normal4((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
-      const float yv = x[0] + (S > 1 ? x[so + c] : 0.f) + off[(long)t * B + b] + sobs * e.x;
+      const int c2 = S2 > 1 ? season_of(L.T + t, S2, L.r2) : 0;
+      const float yv = x[0] + (S > 1 ? x[so + c] : 0.f) + (S2 > 1 ? x[so2 + c2] : 0.f) + off[(long)t * B + b] + sobs * e.x;
       tile[threadIdx.x][q] = fmaf(yv, sg, mu);
       if (so == 2) {                   // level += slope ; slope random walk
         x[0] += x[1];
@@ -491,8 +553,13 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
       x[0] = fmaf(sl, e.y, x[0]);
       if (season_change(L.T + t, S, r)) {
         const float xi = sdr * e.z;
-        for (int a = so; a < D; ++a) x[a] += xi;
+        for (int a = so; a < so2; ++a) x[a] += xi;
         x[so + c] -= (float)S * xi;    // net -(S-1) xi on the season just observed
+      }
+      if (season_change(L.T + t, S2, L.r2)) {   // second seasonal component: its own drift draw
+        const float xi = sdr2 * philox_normal4((uint32_t)si, (uint32_t)t, 1u, TAG_FORECAST, seed).x;
+        for (int a = so2; a < D; ++a) x[a] += xi;
+        x[so2 + c2] -= (float)S2 * xi;
       }
     }
     __syncthreads();
@@ -540,10 +607,15 @@ int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, floa
   const long B = (long)L->N * L->G;
   const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
   const int Dl = big_D(*L);
-#define CI_BIG_EVAL(NC)                                                                                    \
-  {                                                                                                        \
-    if (int e = big_attr(k_eval_big<NC>, smem)) return e;                                                  \
-    k_eval_big<NC><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape); \
+#define CI_BIG_EVAL(NC)                                                                                           \
+  {                                                                                                               \
+    if (L->S2 > 1) {                                                                                              \
+      if (int e = big_attr(k_eval_big<NC, true>, smem)) return e;                                                 \
+      k_eval_big<NC, true><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape);  \
+    } else {                                                                                                      \
+      if (int e = big_attr(k_eval_big<NC, false>, smem)) return e;                                                \
+      k_eval_big<NC, false><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape); \
+    }                                                                                                             \
   }
   if (Dl <= 32) CI_BIG_EVAL(1) else if (Dl <= 64) CI_BIG_EVAL(2) else CI_BIG_EVAL(3)
 #undef CI_BIG_EVAL
@@ -557,10 +629,15 @@ int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, fl
   const long B = (long)L->N * L->G;
   const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
   const int Dl = big_D(*L);
-#define CI_BIG_FILTER(NC)                                                                              \
-  {                                                                                                    \
-    if (int e = big_attr(k_filter_big<NC>, smem)) return e;                                            \
-    k_filter_big<NC><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, pm, pv, fs);     \
+#define CI_BIG_FILTER(NC)                                                                                  \
+  {                                                                                                        \
+    if (L->S2 > 1) {                                                                                       \
+      if (int e = big_attr(k_filter_big<NC, true>, smem)) return e;                                        \
+      k_filter_big<NC, true><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, pm, pv, fs);  \
+    } else {                                                                                               \
+      if (int e = big_attr(k_filter_big<NC, false>, smem)) return e;                                       \
+      k_filter_big<NC, false><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, pm, pv, fs); \
+    }                                                                                                      \
   }
   if (Dl <= 32) CI_BIG_FILTER(1) else if (Dl <= 64) CI_BIG_FILTER(2) else CI_BIG_FILTER(3)
 #undef CI_BIG_FILTER

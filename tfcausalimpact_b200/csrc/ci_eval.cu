@@ -182,27 +182,30 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
   }
 }
 
-__global__ void k_params_forward(int N, int G, int k, int S, int flags, const float* __restrict__ sconst,
+__global__ void k_params_forward(ci_layout L, const float* __restrict__ sconst,
                                  const float* __restrict__ u, float* __restrict__ beta,
                                  float* __restrict__ scal) {
+  const int N = L.N, G = L.G, k = L.k, S = L.S, flags = L.flags;
   const long B = (long)N * G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / G);
-  if (flags == 0) {
+  if (flags == 0 && L.S2 <= 1) {
     LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, N, beta + b, B);
     scal[0 * B + b] = ls.R;
     scal[1 * B + b] = ls.ql;
     scal[2 * B + b] = ls.qd;
     scal[3 * B + b] = ls.lp0;
     scal[4 * B + b] = 0.f;
+    scal[5 * B + b] = 0.f;
   } else {
-    GenScalars ls = params_forward_gen(u + b, B, k, S, flags, sconst + n, N, beta + b, B);
+    GenScalars ls = params_forward_gen(u + b, B, k, S, flags, sconst + n, N, beta + b, B, L.S2);
     scal[0 * B + b] = ls.R;
     scal[1 * B + b] = ls.ql;
     scal[2 * B + b] = ls.qd;
     scal[3 * B + b] = ls.lp0;
     scal[4 * B + b] = ls.qs;     // slope variance (LocalLinearTrend)
+    scal[5 * B + b] = ls.qd2;    // drift variance of the second seasonal component
   }
 }
 
@@ -252,8 +255,7 @@ void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, flo
 void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
                            cudaStream_t st) {
   const long B = (long)L->N * L->G;
-  k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(L->N, L->G, L->k, L->S, L->flags, D->d_sconst, d_u, beta,
-                                                                scal);
+  k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(*L, D->d_sconst, d_u, beta, scal);
 }
 
 template <int S, bool STAGED, bool EFF>
@@ -377,14 +379,15 @@ __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const 
   XY[i] = v;
 }
 
-__global__ void k_constrain(int N, int G, int k, int S, int flags, const float* __restrict__ sconst,
+__global__ void k_constrain(ci_layout L, const float* __restrict__ sconst,
                             const float* __restrict__ u, float* __restrict__ theta) {
+  const int N = L.N, G = L.G, k = L.k, S = L.S, flags = L.flags;
   const long B = (long)N * G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / G);
-  if (flags == 0) params_constrain_lane(u + b, B, k, S, sconst[SC_SD * N + n], theta + b, B);
-  else params_constrain_gen(u + b, B, k, S, flags, sconst[SC_SD * N + n], theta + b, B);
+  if (flags == 0 && L.S2 <= 1) params_constrain_lane(u + b, B, k, S, sconst[SC_SD * N + n], theta + b, B);
+  else params_constrain_gen(u + b, B, k, S, flags, sconst[SC_SD * N + n], theta + b, B, L.S2);
 }
 
 }  // namespace ci
@@ -443,8 +446,7 @@ int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* 
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_sconst && d_u && d_theta, "NULL pointer");
   const long B = (long)L->N * L->G;
-  k_constrain<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(L->N, L->G, L->k, L->S, L->flags, D->d_sconst,
-                                                                            d_u, d_theta);
+  k_constrain<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*L, D->d_sconst, d_u, d_theta);
   CI_CHECK_LAUNCH();
   return CI_OK;
 }

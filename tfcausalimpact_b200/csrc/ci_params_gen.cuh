@@ -7,7 +7,9 @@
 //              level scale: sqrt-InverseGamma (model.py:284-285) | LogNormal(log(.05 sd), 3)
 //              (tfp.sts.LocalLevel / LocalLinearTrend default)                      CI_FLAG_LEVEL_LOGNORMAL / LLT
 //              slope scale: LogNormal(log(.05 sd), 3); dense weights: StudentT(5, 0, 10) [TFP defaults]
-// Parameter order = tfp `model.parameters`: observation_noise_scale, trend scales, regression, drift.
+//   seasonal   up to TWO tfp.sts.Seasonal components (S, r) and (S2, r2), each with its own drift scale
+//              ~ LogNormal(log(.01 sd), 3) (notebooks/getting_started.ipynb cell 116: Month + Year)
+// Parameter order = tfp `model.parameters`: observation_noise_scale, trend scales, regression, drift(s).
 // Every constant of the log-density is evaluated explicitly here (this path is not hot), so
 // SC_PRIOR_CONST is not used.  These are the custom-model examples of the reference's docs
 // (/root/reference/causalimpact/main.py:186-252, notebooks/getting_started.ipynb cell 44).
@@ -22,14 +24,14 @@
 
 namespace ci {
 
-CI_HD int num_params_gen(int k, int S, int flags) {
+CI_HD int num_params_gen(int k, int S, int flags, int S2 = 1) {
   const int trend = (flags & CI_FLAG_LLT) ? 2 : 1;
   const int reg = k > 0 ? ((flags & CI_FLAG_DENSE_REG) ? k : 2 + 3 * k) : 0;
-  return 1 + trend + reg + (S > 1 ? 1 : 0);
+  return 1 + trend + reg + (S > 1 ? 1 : 0) + (S2 > 1 ? 1 : 0);
 }
 
 struct GenScalars {
-  float R, ql, qs, qd, lp0;
+  float R, ql, qs, qd, lp0, qd2;
 };
 
 // log density of theta = sd softplus(u) under the scale prior + log |d theta / d u|, and its
@@ -61,7 +63,8 @@ CI_HD ScaleTerm scale_term(float u, float sd, bool lognormal, float ig_b, float 
 
 // Forward: returns variances + log prior/log-det, writes beta (stride ldb).
 CI_HD GenScalars params_forward_gen(const float* __restrict__ u, long ld, int k, int S, int flags,
-                                    const float* __restrict__ sc, long scld, float* __restrict__ beta, long ldb) {
+                                    const float* __restrict__ sc, long scld, float* __restrict__ beta, long ldb,
+                                    int S2 = 1) {
   const float sd = sc[SC_SD * scld];
   const float mu01 = sc[SC_DRIFT_MU * scld];                 // log(0.01 sd)
   const float mu05 = mu01 + 1.6094379124341003f;             // log(0.05 sd)
@@ -76,6 +79,7 @@ CI_HD GenScalars params_forward_gen(const float* __restrict__ u, long ld, int k,
   o.ql = sl.theta * sl.theta;
   o.qs = 0.f;
   o.qd = 0.f;
+  o.qd2 = 0.f;
   if (llt) {
     const ScaleTerm ss = scale_term(u[(long)i++ * ld], sd, true, 0.f, mu05, 3.f, 0.f);
     lp += ss.lp;
@@ -113,6 +117,13 @@ CI_HD GenScalars params_forward_gen(const float* __restrict__ u, long ld, int k,
     lp += sdft.lp;
     const float q = sdft.theta * (1.0f / S);
     o.qd = q * q;
+    ++i;
+  }
+  if (S2 > 1) {
+    const ScaleTerm sdft = scale_term(u[(long)i * ld], sd, true, 0.f, mu01, 3.f, 0.f);
+    lp += sdft.lp;
+    const float q = sdft.theta * (1.0f / S2);
+    o.qd2 = q * q;
   }
   o.lp0 = lp;
   return o;
@@ -122,7 +133,8 @@ CI_HD GenScalars params_forward_gen(const float* __restrict__ u, long ld, int k,
 // variances (Rb, qlb, qsb, qdb) and beta_bar (stride ldb).
 CI_HD void params_backward_gen(const float* __restrict__ u, long ld, int k, int S, int flags,
                                const float* __restrict__ sc, long scld, const float* __restrict__ beta_bar, long ldb,
-                               float Rb, float qlb, float qsb, float qdb, float* __restrict__ grad) {
+                               float Rb, float qlb, float qsb, float qdb, float* __restrict__ grad, int S2 = 1,
+                               float qd2b = 0.f) {
   const float sd = sc[SC_SD * scld];
   const float mu01 = sc[SC_DRIFT_MU * scld];
   const float mu05 = mu01 + 1.6094379124341003f;
@@ -168,12 +180,16 @@ CI_HD void params_backward_gen(const float* __restrict__ u, long ld, int k, int 
       i += 2 + 3 * k;
     }
   }
-  if (S > 1) grad[(long)i * ld] = scale_term(u[(long)i * ld], sd, true, 0.f, mu01, 3.f, qdb * (1.0f / (S * S))).dlp_du;
+  if (S > 1) {
+    grad[(long)i * ld] = scale_term(u[(long)i * ld], sd, true, 0.f, mu01, 3.f, qdb * (1.0f / (S * S))).dlp_du;
+    ++i;
+  }
+  if (S2 > 1) grad[(long)i * ld] = scale_term(u[(long)i * ld], sd, true, 0.f, mu01, 3.f, qd2b * (1.0f / (S2 * S2))).dlp_du;
 }
 
 // Constrained values theta (same order / stride) from u.
 CI_HD void params_constrain_gen(const float* __restrict__ u, long ld, int k, int S, int flags, float sd,
-                                float* __restrict__ theta, long ldo) {
+                                float* __restrict__ theta, long ldo, int S2 = 1) {
   const int nscale = 1 + ((flags & CI_FLAG_LLT) ? 2 : 1);
   int i = 0;
   for (; i < nscale; ++i) theta[(long)i * ldo] = sd * softplus(u[(long)i * ld]);
@@ -185,7 +201,11 @@ CI_HD void params_constrain_gen(const float* __restrict__ u, long ld, int k, int
       for (int j = 0; j < k; ++j, ++i) theta[(long)i * ldo] = u[(long)i * ld];
     }
   }
-  if (S > 1) theta[(long)i * ldo] = sd * softplus(u[(long)i * ld]);
+  if (S > 1) {
+    theta[(long)i * ldo] = sd * softplus(u[(long)i * ld]);
+    ++i;
+  }
+  if (S2 > 1) theta[(long)i * ldo] = sd * softplus(u[(long)i * ld]);
 }
 
 }  // namespace ci

@@ -18,7 +18,7 @@ class DeviceBatch:
     """N independent series sharing one state-space layout, resident on one GPU."""
 
     def __init__(self, y, X=None, Tf=0, nseasons=1, season_duration=1, prior_level_sd=0.01,
-                 device=None, flags=0):
+                 device=None, flags=0, nseasons2=0, season_duration2=0):
         nt.require_cuda()
         self.lib = nt.lib()
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
@@ -29,6 +29,8 @@ class DeviceBatch:
         self.N, self.T = self.y.shape
         self.Tf, self.S, self.r = int(Tf), int(nseasons), int(season_duration)
         self.flags = int(flags)      # wider model set (_native.FLAG_*): runs on the warp-per-lane kernels
+        # second Seasonal component of a custom model (Sum([..., Seasonal(S), Seasonal(S2)])); 0 = none
+        self.S2, self.r2 = (int(nseasons2), int(season_duration2) or 1) if int(nseasons2) > 1 else (0, 0)
         if X is None:
             self.k = 0
         else:
@@ -39,7 +41,7 @@ class DeviceBatch:
                 f'design matrix must be [N, T+Tf, k], got {tuple(X.shape)}'
             self.k = X.shape[2]
         self.Tpad = (self.T + self.Tf + 3) // 4 * 4
-        self.P = nt.num_params(self.k, self.S, self.flags)
+        self.P = nt.num_params(self.k, self.S, self.flags, self.S2)
         self.sconst = torch.empty((8, self.N), dtype=torch.float32, device=self.device)
         L = self.layout(1)
         with torch.cuda.device(self.device):
@@ -56,7 +58,7 @@ class DeviceBatch:
 
     # ------------------------------------------------------------------------------------------
     def layout(self, G):
-        return nt.CiLayout(self.N, int(G), self.T, self.Tf, self.k, self.S, self.r, self.Tpad, self.flags)
+        return nt.CiLayout(self.N, int(G), self.T, self.Tf, self.k, self.S, self.r, self.Tpad, self.flags, self.S2, self.r2)
 
     def data(self):
         return nt.CiData(nt.ptr(self.y).value, nt.ptr(self.X).value,
@@ -240,13 +242,14 @@ class DeviceBatch:
         u[0:nscale] = sp_inv(theta[0:nscale] / sd)
         if k > 0 and not (self.flags & nt.FLAG_DENSE_REG):
             u[nscale:nscale + 2 + 2 * k] = sp_inv(theta[nscale:nscale + 2 + 2 * k])
-        if self.S > 1:
-            u[self.P - 1] = sp_inv(theta[self.P - 1] / sd[0])
+        nseas = (1 if self.S > 1 else 0) + (1 if self.S2 > 1 else 0)
+        if nseas:
+            u[self.P - nseas:] = sp_inv(theta[self.P - nseas:] / sd)
         return u.contiguous()
 
 
 def _layout_for(N, T, Tf):
-    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 3) // 4 * 4, 0)
+    return nt.CiLayout(int(N), 1, int(T), int(Tf), 0, 1, 1, (int(T) + int(Tf) + 3) // 4 * 4, 0, 0, 0)
 
 
 def reduce_inferences(y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean, alpha):

@@ -174,8 +174,8 @@ class Seasonal(Component):
 
 class Sum:
     """Additive structural time-series model the kernels implement: one trend (LocalLevel |
-    LocalLinearTrend) [+ one regression (SparseLinearRegression | LinearRegression)] [+ Seasonal] +
-    observation noise.  Built without `observation_noise_scale_prior` it takes tfp.sts.Sum's default,
+    LocalLinearTrend) [+ one regression (SparseLinearRegression | LinearRegression)] [+ up to two Seasonal
+    components, e.g. the notebook's Month + Year (getting_started.ipynb cell 116)] + observation noise.  Built without `observation_noise_scale_prior` it takes tfp.sts.Sum's default,
     LogNormal(log(.01 sd), 2)."""
 
     def __init__(self, components, observed_time_series=None, observation_noise_scale_prior: Optional[Prior] = None,
@@ -203,10 +203,15 @@ class Sum:
                     'LocalLevel | LocalLinearTrend, SparseLinearRegression | LinearRegression and Seasonal '
                     'only; other tfp.sts components are rejected (no fallback).')
         if kinds.count(LocalLevel) + kinds.count(LocalLinearTrend) != 1 or \
-                kinds.count(SparseLinearRegression) + kinds.count(LinearRegression) > 1 or kinds.count(Seasonal) > 1:
+                kinds.count(SparseLinearRegression) + kinds.count(LinearRegression) > 1 or kinds.count(Seasonal) > 2:
             raise ValueError('Supported model = exactly one trend (LocalLevel or LocalLinearTrend), at most one '
-                             'regression (SparseLinearRegression or LinearRegression) and at most one Seasonal '
-                             'component.')
+                             'regression (SparseLinearRegression or LinearRegression) and at most two Seasonal '
+                             'components.')
+        seas = [c for c in self.components if isinstance(c, Seasonal)]
+        if len(seas) == 2 and (seas[0].num_seasons <= 1 or seas[1].num_seasons <= 1):
+            raise ValueError('Each of two Seasonal components needs num_seasons > 1.')
+        if len(seas) == 2 and seas[0].name == seas[1].name:
+            raise ValueError('Two Seasonal components need distinct names (their parameters are keyed by name).')
         order = {LocalLevel: 0, LocalLinearTrend: 0, SparseLinearRegression: 1, LinearRegression: 1, Seasonal: 2}
         if [order[k] for k in kinds] != sorted(order[k] for k in kinds):
             raise ValueError('Components must be ordered trend, regression, seasonal (the parameter order of the '
@@ -266,7 +271,10 @@ class Sum:
         key = (y.tobytes(), int(Tf))
         if self._engine is not None and self._engine[0] == key:
             return self._engine[1]
-        reg, sea = self._regression(), self._component(Seasonal)
+        reg = self._regression()
+        seas = [c for c in self.components if isinstance(c, Seasonal)]
+        sea = seas[0] if seas else None
+        sea2 = seas[1] if len(seas) > 1 else None
         X = None
         if reg is not None:
             X = reg.design_matrix.to_dense()
@@ -276,7 +284,9 @@ class Sum:
         obs_pr = self.observation_noise_scale_prior
         db = DeviceBatch(y[None, :], X, Tf=Tf, nseasons=sea.num_seasons if sea else 1,
                          season_duration=sea.num_steps_per_season if sea else 1,
-                         prior_level_sd=self.prior_level_sd, flags=self.flags)
+                         prior_level_sd=self.prior_level_sd, flags=self.flags,
+                         nseasons2=sea2.num_seasons if sea2 else 0,
+                         season_duration2=sea2.num_steps_per_season if sea2 else 0)
         if obs_pr.family == 'SqrtInverseGamma':
             db.set_obs_prior_scale(obs_pr.params['scale'])
         self._engine = (key, db)
