@@ -265,9 +265,10 @@ def main():
     accept = float(stats[0].mean().item())
     finite = bool(torch.isfinite(draws_buf[:args.steps]).all().item())
     draws_per_s = world * B * args.steps / (ms * 1e-3)
-    # launches: per transition begin + L * eval kernel (leapfrog kick/drift fused in) + end; + reset, initial eval, stats
+    # launches: per transition one boundary kernel (end of the previous + begin of this transition) + L * eval kernel
+    # (leapfrog kick/drift fused in); + reset, initial eval, closing boundary kernel, stats
     kern_per_eval = int(lib.ci_eval_num_kernels(ctypes.byref(db.layout(C)))) if hasattr(lib, 'ci_eval_num_kernels') else 5
-    launches = args.steps * (2 + LEAPFROG * kern_per_eval) + 2 + kern_per_eval
+    launches = args.steps * (1 + LEAPFROG * kern_per_eval) + 3 + kern_per_eval
 
     # ---- dominant kernel alone: Kalman log-prob + gradient evaluation ------------------------------
     lp = torch.empty(B, dtype=torch.float32, device=dev)

@@ -181,69 +181,110 @@ __global__ void k_hmc_reset(long B, float* __restrict__ lane) {
   lane[HL_ACC_SAMP * B + b] = 0.f;
 }
 
-// Momentum draw, initial Hamiltonian, first half kick and first drift.
-__global__ void k_hmc_begin(long B, int P, uint32_t it, uint64_t seed, const float* __restrict__ step0,
-                            const float* __restrict__ u, const float* __restrict__ g,
-                            float* __restrict__ uu, float* __restrict__ pp, float* __restrict__ lane) {
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float fac = expf(lane[HL_LOGFAC * B + b]);
-  float ke = 0.f;
-  for (int p = 0; p < P; ++p) {
-    const long i = (long)p * B + b;
-    const float mom = philox_normal4((uint32_t)b, (uint32_t)p, it, TAG_HMC_MOM, seed).x;
-    ke = fmaf(mom, mom, ke);
-    const float eps = step0[i] * fac;
-    const float ph = fmaf(0.5f * eps, g[i], mom);
-    pp[i] = ph;
-    uu[i] = fmaf(eps, ph, u[i]);
-  }
-  lane[HL_H0 * B + b] = -lane[HL_LP * B + b] + 0.5f * ke;
-}
+// One kernel per transition boundary: [end of transition `it`] + [begin of transition `it + 1`].
+//   end   : kinetic energy of the proposal, Metropolis accept, state selection, dual averaging, draw output
+//   begin : momentum draw, initial Hamiltonian, first half kick and first drift of the next transition
+// Block = 32 lanes x HMC_PG parameter groups (parameter p is handled by group p % HMC_PG), so every
+// access is a coalesced 128-byte row of the [P][B] arrays and a lane's P parameters are spread over
+// HMC_PG threads; the per-lane sums are reduced through shared memory in a fixed order (deterministic).
+// Fusing the two halves re-uses the selected (u, g) from registers instead of re-reading them.
+constexpr int HMC_PG = 8;
 
-// Metropolis accept, state selection, dual averaging, draw output.
-__global__ void k_hmc_end(long B, int P, uint32_t it_rng, int it, int num_warmup, int num_adapt,
-                          float target_accept, uint64_t seed, float* __restrict__ u, float* __restrict__ g,
-                          const float* __restrict__ uu, const float* __restrict__ gg,
-                          const float* __restrict__ pp, float* __restrict__ lane, float* __restrict__ draw) {
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float ke = 0.f;
-  for (int p = 0; p < P; ++p) {
-    const float m = pp[(long)p * B + b];
-    ke = fmaf(m, m, ke);
-  }
-  const float lp_new = lane[HL_LPNEW * B + b];
-  const float h1 = -lp_new + 0.5f * ke;
-  float log_acc = lane[HL_H0 * B + b] - h1;
-  if (!isfinite(log_acc)) log_acc = -INFINITY;
-  const float un = philox_uniform4((uint32_t)b, 0u, it_rng, TAG_HMC_ACC, seed).x;
-  const bool acc = logf(un) < log_acc;
-  if (acc) {
-    for (int p = 0; p < P; ++p) {
-      const long i = (long)p * B + b;
-      u[i] = uu[i];
-      g[i] = gg[i];
+struct HmcTurn {
+  int do_end, do_begin;
+  int it, num_warmup, num_adapt;    // transition being closed (end half)
+  uint32_t it_rng_end, it_rng_begin;
+  float target_accept;
+  uint64_t seed;
+};
+
+__global__ void __launch_bounds__(32 * HMC_PG)
+k_hmc_turn(long B, int P, HmcTurn a, const float* __restrict__ step0, float* __restrict__ u, float* __restrict__ g,
+           float* __restrict__ uu, float* __restrict__ gg, float* __restrict__ pp, float* __restrict__ lane,
+           float* __restrict__ draw) {
+  __shared__ float red[HMC_PG][32];
+  __shared__ float bc[2][32];    // per-lane broadcast: accept flag, step factor
+  const int x = threadIdx.x, y = threadIdx.y;
+  const long b = (long)blockIdx.x * 32 + x;
+  const bool live = b < B;
+  bool acc = false;
+  if (a.do_end) {
+    float ke = 0.f;
+    if (live)
+      for (int p = y; p < P; p += HMC_PG) {
+        const float m = pp[(long)p * B + b];
+        ke = fmaf(m, m, ke);
+      }
+    red[y][x] = ke;
+    __syncthreads();
+    if (y == 0 && live) {
+      float kes = 0.f;
+#pragma unroll
+      for (int q = 0; q < HMC_PG; ++q) kes += red[q][x];
+      const float lp_new = lane[HL_LPNEW * B + b];
+      const float h1 = -lp_new + 0.5f * kes;
+      float log_acc = lane[HL_H0 * B + b] - h1;
+      if (!isfinite(log_acc)) log_acc = -INFINITY;
+      const float un = philox_uniform4((uint32_t)b, 0u, a.it_rng_end, TAG_HMC_ACC, a.seed).x;
+      const bool ac = logf(un) < log_acc;
+      if (ac) lane[HL_LP * B + b] = lp_new;
+      if (a.it < a.num_warmup) lane[HL_ACC_WARM * B + b] += ac ? 1.f : 0.f;
+      else lane[HL_ACC_SAMP * B + b] += ac ? 1.f : 0.f;
+      if (a.it < a.num_adapt) {
+        // tfp.mcmc.DualAveragingStepSizeAdaptation defaults: exploration_shrinkage 0.05,
+        // step_count_smoothing 10, decay_rate 0.75, shrinkage target log(10 eps0).
+        const float p_acc = expf(fminf(log_acc, 0.f));
+        const float err = lane[HL_ERRSUM * B + b] + a.target_accept - p_acc;
+        lane[HL_ERRSUM * B + b] = err;
+        const float t = (float)a.it + 1.0f;
+        const float log_x = 2.302585092994046f - err * sqrtf(t) / ((t + 10.0f) * 0.05f);
+        const float eta = powf(t, -0.75f);
+        const float avg = eta * log_x + (1.0f - eta) * lane[HL_LOGFAC_AVG * B + b];
+        lane[HL_LOGFAC_AVG * B + b] = avg;
+        lane[HL_LOGFAC * B + b] = (a.it < a.num_adapt - 1) ? log_x : avg;
+      }
+      bc[0][x] = ac ? 1.f : 0.f;
     }
-    lane[HL_LP * B + b] = lp_new;
+    __syncthreads();
+    acc = live && bc[0][x] != 0.f;
   }
-  if (it < num_warmup) lane[HL_ACC_WARM * B + b] += acc ? 1.f : 0.f;
-  else lane[HL_ACC_SAMP * B + b] += acc ? 1.f : 0.f;
-  if (it < num_adapt) {
-    // tfp.mcmc.DualAveragingStepSizeAdaptation defaults: exploration_shrinkage 0.05,
-    // step_count_smoothing 10, decay_rate 0.75, shrinkage target log(10 eps0).
-    const float p_acc = expf(fminf(log_acc, 0.f));
-    const float err = lane[HL_ERRSUM * B + b] + target_accept - p_acc;
-    lane[HL_ERRSUM * B + b] = err;
-    const float t = (float)it + 1.0f;
-    const float log_x = 2.302585092994046f - err * sqrtf(t) / ((t + 10.0f) * 0.05f);
-    const float eta = powf(t, -0.75f);
-    const float avg = eta * log_x + (1.0f - eta) * lane[HL_LOGFAC_AVG * B + b];
-    lane[HL_LOGFAC_AVG * B + b] = avg;
-    lane[HL_LOGFAC * B + b] = (it < num_adapt - 1) ? log_x : avg;
-  }
-  if (draw) {
-    for (int p = 0; p < P; ++p) draw[(long)p * B + b] = u[(long)p * B + b];
+  if (y == 0 && live && a.do_begin) bc[1][x] = expf(lane[HL_LOGFAC * B + b]);
+  __syncthreads();
+  const float fac = (a.do_begin && live) ? bc[1][x] : 1.f;
+  float ke2 = 0.f;
+  if (live)
+    for (int p = y; p < P; p += HMC_PG) {
+      const long i = (long)p * B + b;
+      float un, gn;
+      if (acc) {
+        un = uu[i];
+        gn = gg[i];
+        u[i] = un;
+        g[i] = gn;
+      } else {
+        un = u[i];
+        gn = g[i];
+      }
+      if (a.do_end && draw) draw[i] = un;
+      if (a.do_begin) {
+        const float mom = philox_normal4((uint32_t)b, (uint32_t)p, a.it_rng_begin, TAG_HMC_MOM, a.seed).x;
+        ke2 = fmaf(mom, mom, ke2);
+        const float eps = step0[i] * fac;
+        const float ph = fmaf(0.5f * eps, gn, mom);
+        pp[i] = ph;
+        uu[i] = fmaf(eps, ph, un);
+      }
+    }
+  if (a.do_begin) {
+    __syncthreads();          // red[] is free again (its readers passed the barriers above)
+    red[y][x] = ke2;
+    __syncthreads();
+    if (y == 0 && live) {
+      float kes = 0.f;
+#pragma unroll
+      for (int q = 0; q < HMC_PG; ++q) kes += red[q][x];
+      lane[HL_H0 * B + b] = -lane[HL_LP * B + b] + 0.5f * kes;
+    }
   }
 }
 
@@ -342,9 +383,23 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
   k_hmc_reset<<<gl, 128, 0, st>>>(B, ws.lane);
   // log-prob and gradient at the initial state (cached between transitions, as TFP does)
   if (int e = launch_eval(L, D, d_u, ws.lane + HL_LP * B, ws.g, ws.ev, st)) return e;
-  for (int it = 0; it < num_warmup + num_results; ++it) {
-    const uint32_t it_rng = (uint32_t)(iter_offset + it);
-    k_hmc_begin<<<gl, 128, 0, st>>>(B, P, it_rng, seed, d_step0, d_u, ws.g, ws.uu, ws.pp, ws.lane);
+  const int n_it = num_warmup + num_results;
+  const dim3 tb(32, HMC_PG), tg((unsigned)((B + 31) / 32));
+  for (int it = 0; it <= n_it; ++it) {
+    // boundary kernel: closes transition it - 1 (accept, adaptation, draw) and opens transition it
+    HmcTurn a;
+    a.do_end = it > 0;
+    a.do_begin = it < n_it;
+    a.it = it - 1;
+    a.num_warmup = num_warmup;
+    a.num_adapt = num_adapt;
+    a.it_rng_end = (uint32_t)(iter_offset + it - 1);
+    a.it_rng_begin = (uint32_t)(iter_offset + it);
+    a.target_accept = target_accept;
+    a.seed = seed;
+    float* draw = (it > 0 && it - 1 >= num_warmup) ? d_draws + (size_t)(it - 1 - num_warmup) * P * B : nullptr;
+    k_hmc_turn<<<tg, tb, 0, st>>>(B, P, a, d_step0, d_u, ws.g, ws.uu, ws.gg, ws.pp, ws.lane, draw);
+    if (it == n_it) break;
     for (int l = 0; l < num_leapfrog; ++l) {
       // kick (and, unless last, drift) fused into the evaluation kernel's epilogue
       LeapArgs lf;
@@ -355,9 +410,6 @@ int ci_hmc_run(const ci_layout* L, const ci_data* D, float* d_u, const float* d_
       lf.last = (l == num_leapfrog - 1);
       if (int e = launch_eval(L, D, ws.uu, ws.lane + HL_LPNEW * B, ws.gg, ws.ev, st, &lf)) return e;
     }
-    float* draw = it >= num_warmup ? d_draws + (size_t)(it - num_warmup) * P * B : nullptr;
-    k_hmc_end<<<gl, 128, 0, st>>>(B, P, it_rng, it, num_warmup, num_adapt, target_accept, seed, d_u, ws.g, ws.uu,
-                                  ws.gg, ws.pp, ws.lane, draw);
   }
   if (d_stats) k_hmc_stats<<<gl, 128, 0, st>>>(B, num_warmup, num_results, ws.lane, d_stats);
   CI_CHECK_LAUNCH();
