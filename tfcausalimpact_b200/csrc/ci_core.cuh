@@ -37,6 +37,19 @@ CI_HD float fast_log(float x) {
 #endif
 }
 
+// log2 of an innovation variance (never denormal: s >= sigma_obs^2 > 0): a single MUFU.LG2
+CI_HD float fast_log2(float x) {
+#if defined(__CUDA_ARCH__) && defined(CI_LOG2_BUILTIN)
+  return __log2f(x);
+#elif defined(__CUDA_ARCH__)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return log2f(x);
+#endif
+}
+
 CI_HD float softplus(float u) {
   // log(1 + e^u), stable on both tails
   return (u > 0.f ? u : 0.f) + log1pf(expf(-fabsf(u)));

@@ -42,6 +42,7 @@ struct XStaged {
   long cstride;          // floats between consecutive chunks = N * (k + 1) * CI_TC
 
   __device__ __forceinline__ void issue(int tc) const {   // lane 0 of the warp
+    // (measured: dropping this proxy fence gains 0.2 % -- kept, the cross-proxy write-after-read stays explicit)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -135,6 +136,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
   const long nwarp = (B + 31) / 32;
   float* tape_eff = tape + (b >> 5) * ((ES + 1) * 32) + (b & 31);
   const int tstep_eff = (int)(nwarp * ((ES + 1) * 32));
+  const int pfrow = (int)(threadIdx.x & 31) < ES + 1 ? (int)(threadIdx.x & 31) : -1;   // tape row this lane prefetches
   if (STAGED) {
     const int w = threadIdx.x >> 5;
     const long bw0 = b - (threadIdx.x & 31);              // first lane of this warp
@@ -162,7 +164,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
     if (valid) {
       if (EFF)
         eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
-                                            logp + b, grad + b);
+                                            logp + b, grad + b, pfrow);
       else
         eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b,
                      grad + b);
@@ -175,7 +177,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
     XDirect xs{XY + (long)n * stride, cstride};
     if (EFF)
       eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
-                                          logp + b, grad + b);
+                                          logp + b, grad + b, pfrow);
     else
       eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
     leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);

@@ -217,17 +217,20 @@ struct EffLane {
   const int T, k;
   float* __restrict__ sb;   // beta_bar / MINUS beta column, element j at sb[j * SBLD]
   float* __restrict__ sr;
-  float* tp;
+  float* tp;            // this lane's column of the tape entry being written / read
   const int tstep;
+  const int pfoff;      // reverse sweep: offset (floats) from tp to the line this lane prefetches, 0 = none
   const float R, ql, q11;
   EState<S> st;
-  float acc = 0.f, comp = 0.f;
-  int nobs = 0;
+  float acc = 0.f, quad = 0.f;   // sum of log2 s_t and of v_t^2 / s_t over the observed steps
+  int nmask = 0;                 // masked (missing) steps; the common observed path carries no counter
   float Rb = 0.f, qlb = 0.f, qdb = 0.f;
+  float sig = 0.f;   // 1^T Pbar_seas 1, carried incrementally through the reverse sweep
 
   CI_HD EffLane(XS& xs_, int T_, int k_, float* sb_, float* sr_, float* tape, int tstep_, float R_, float ql_,
-                float qd_)
-      : xs(xs_), T(T_), k(k_), sb(sb_), sr(sr_), tp(tape), tstep(tstep_), R(R_), ql(ql_), q11(qd_) {}
+                float qd_, int pfrow_)
+      : xs(xs_), T(T_), k(k_), sb(sb_), sr(sr_), tp(tape), tstep(tstep_),
+        pfoff(pfrow_ >= 0 ? pfrow_ * TQ - CI_TAPE_AHEAD * tstep_ : 0), R(R_), ql(ql_), q11(qd_) {}
   CI_HD int nchunk() const { return (T + CI_TC - 1) / CI_TC; }
 
   // r_i = (y_i - mean) + sum_j (-beta_j) X_ji for the CI_TC steps of chunk tc (sb holds -beta, row k
@@ -327,13 +330,11 @@ struct EffLane {
 #pragma unroll
       for (int q = 0; q < S; ++q) tp[q * TQ] = g[q];
       tp[S * TQ] = v;
-      const float term = fast_log(s) + v * v * is;
-      const float yk = term - comp;
-      const float tk = acc + yk;
-      comp = (tk - acc) - yk;
-      acc = tk;
-      ++nobs;
+      // two plain sums: log2 of the innovation variances (scaled by ln 2 once at the end) and v^2 / s
+      acc += fast_log2(s);
+      quad = fmaf(v * is, v, quad);
     } else {
+      ++nmask;
 #pragma unroll
       for (int q = 0; q < S; ++q) tp[q * TQ] = 0.f;
       tp[S * TQ] = r;
@@ -342,31 +343,28 @@ struct EffLane {
     tp += tstep;
   }
 
-  // tp points at the entry of the step being processed; it was pulled into L2 CI_TAPE_AHEAD steps ago.
+  // The entry of step t was pulled into L2 CI_TAPE_AHEAD steps ago: lane q < S + 1 of the warp prefetches
+  // row q (one 128-byte line per row in the warp-blocked layout), i.e. ONE prefetch instruction per step.
   template <int C>
-  CI_HD float bwd_step(bool more, bool far) {
+  CI_HD float bwd_step(bool far) {
     float cur[D];
 #pragma unroll
     for (int q = 0; q < D; ++q) cur[q] = tp[q * TQ];
-    if (far) {    // pull the entry CI_TAPE_AHEAD steps back from HBM into L2
-#pragma unroll
-      for (int q = 0; q < D; ++q) prefetch_l2((tp - CI_TAPE_AHEAD * tstep) + q * TQ);
-    }
-    (void)more;
-    eb_predict_adj<S, C>(st, qlb, qdb);
+    if (far && pfoff != 0) prefetch_l2(tp + pfoff);
+    eb_predict_adj<S, C>(st, qlb, qdb, sig);
     float rb = 0.f;
     const float v = cur[S];
     if (v == v) {
       float g[D];
-      float gs = 0.f;
+      float gs = cur[1];
 #pragma unroll
       for (int q = 0; q < S; ++q) {
         g[q] = cur[q];
-        if (q >= 1) gs += cur[q];
+        if (q >= 2) gs += cur[q];
       }
       g[S] = -gs;
       const float s = g[0] + g[1 + C] + R;
-      rb = eb_update_adj<S, C>(st, g, s, v, Rb);
+      rb = eb_update_adj<S, C>(st, g, s, v, Rb, sig);
     }
     tp -= tstep;
     return rb;
@@ -379,9 +377,9 @@ struct EffLane {
     else disp_fwd<(C + 1 < S ? C + 1 : C)>(c, r);
   }
   template <int C>
-  CI_HD float disp_bwd(int c, bool more, bool far) {
-    if (C == S - 1 || c == C) return bwd_step<C>(more, far);
-    else return disp_bwd<(C + 1 < S ? C + 1 : C)>(c, more, far);
+  CI_HD float disp_bwd(int c, bool far) {
+    if (C == S - 1 || c == C) return bwd_step<C>(far);
+    else return disp_bwd<(C + 1 < S ? C + 1 : C)>(c, far);
   }
 
   CI_HD void forward() {
@@ -398,7 +396,7 @@ struct EffLane {
     int c = (T - 1) % S;
     for (int t = T - 1; t >= 0; --t) {
       const int i = t & (CI_TC - 1);
-      sr[i] = disp_bwd<0>(c, t > 0, t >= CI_TAPE_AHEAD);
+      sr[i] = disp_bwd<0>(c, t >= CI_TAPE_AHEAD);
       if (i == 0) regress_bwd(t / CI_TC);
       c = (c == 0) ? S - 1 : c - 1;
     }
@@ -412,13 +410,13 @@ struct EffLane {
 template <int S, int TQ, int SBLD, class XS>
 CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs,
                          int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
-                         int tstep, float* __restrict__ logp_out, float* __restrict__ grad) {
+                         int tstep, float* __restrict__ logp_out, float* __restrict__ grad, int pfrow = -1) {
   const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, SBLD, -1.0f);   // sb <- -beta
   using LaneT = EffLane<S, XS, TQ, SBLD>;
-  LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd);
+  LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd, pfrow);
   ef_init<S>(L.st, sc[SC_M0 * scld], sc[SC_P0 * scld]);
   L.forward();
-  const float ll = -0.5f * (L.acc + (float)L.nobs * CI_LOG_2PI);
+  const float ll = -0.5f * (fmaf(L.acc, 0.6931471805599453f, L.quad) + (float)(T - L.nmask) * CI_LOG_2PI);
 
   for (int j = 0; j < k; ++j) sb[j * SBLD] = 0.f;
 #pragma unroll

@@ -85,27 +85,27 @@ CI_HD void ef_predict(EState<S>& k, float ql, float q11, float q1c, float qcc) {
   }
 }
 
-// Adjoint of ef_predict: accumulates dL/dql and dL/dqd = w^T Pbar_seas w.
+// Adjoint of ef_predict: accumulates dL/dql and dL/dqd = w^T Pbar_seas w
+//   = 1^T W 1 - 2 S (W 1)_c + S^2 W_cc   (W = seasonal block of Pbar).
+// `sig` = 1^T W 1 is carried incrementally by eb_update_adj: Pbar only ever changes by sym(gb H^T), which
+// adds sum_{j >= 1} gb_j to the block sum, so the S(S+1)/2-term sum is not recomputed every step.
 template <int S, int C>
-CI_HD void eb_predict_adj(const EState<S>& b, float& qlb, float& qdb) {
+CI_HD void eb_predict_adj(const EState<S>& b, float& qlb, float& qdb, float sig) {
   constexpr int D = S + 1;
   constexpr int J = 1 + C;
   qlb += b.P[tri<D>(0, 0)];
-  float diag = 0.f, offd = 0.f, rowc = 0.f;
+  // two partial sums, seeded with their first terms (0 + x is not folded by the compiler)
+  float r0 = b.P[sym<D>(J, 1)], r1 = D > 2 ? b.P[sym<D>(J, 2)] : 0.f;
 #pragma unroll
-  for (int i = 1; i < D; ++i) {
-    diag += b.P[tri<D>(i, i)];
-    rowc += b.P[sym<D>(J, i)];
-#pragma unroll
-    for (int j = i + 1; j < D; ++j) offd += b.P[tri<D>(i, j)];
+  for (int i = 3; i < D; ++i) {
+    if (i & 1) r0 += b.P[sym<D>(J, i)]; else r1 += b.P[sym<D>(J, i)];
   }
-  // w^T W w = 1^T W 1 - 2 S (W 1)_c + S^2 W_cc
-  qdb += (diag + 2.f * offd) - (2.f * S) * rowc + (float)(S * S) * b.P[tri<D>(J, J)];
+  qdb += fmaf((float)(S * S), b.P[tri<D>(J, J)], fmaf(-(2.f * S), r0 + r1, sig));
 }
 
 // Adjoint of ef_update given the taped (g, v) and recomputed s.  Returns rbar = dL/dr_t.
 template <int S, int C>
-CI_HD float eb_update_adj(EState<S>& b, const float (&g)[S + 1], float s, float v, float& Rb) {
+CI_HD float eb_update_adj(EState<S>& b, const float (&g)[S + 1], float s, float v, float& Rb, float& sig) {
   constexpr int D = S + 1;
   constexpr int J = 1 + C;
   const float is = rcp(s);
@@ -129,6 +129,14 @@ CI_HD float eb_update_adj(EState<S>& b, const float (&g)[S + 1], float s, float 
   float gb[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) gb[i] = fmaf(b.m[i], vis, fmaf(-2.f * is, Pg[i], (i == 0 || i == J) ? sb : 0.f));
+  {
+    float s0 = gb[1], s1 = D > 2 ? gb[2] : 0.f;
+#pragma unroll
+    for (int j = 3; j < D; ++j) {
+      if (j & 1) s0 += gb[j]; else s1 += gb[j];
+    }
+    sig += s0 + s1;
+  }
   // Pbar += sym(gb H^T), H = e_0 + e_J
   b.P[tri<D>(0, 0)] += gb[0];
   b.P[tri<D>(J, J)] += gb[J];
