@@ -23,8 +23,18 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for _ in range(it): db.logp_grad(u, lp, gr)
 e1.record(); torch.cuda.synchronize()
-print('%%s %%.4f ms  lp_sum=%%.6e grad_abs=%%.6e' %% (os.path.basename(sys.argv[1]), e0.elapsed_time(e1) / it,
-      float(lp.double().sum()), float(gr.double().abs().sum())))
+ms_eval = e0.elapsed_time(e1) / it
+# one HMC transition = 15 evaluations with the fused leapfrog epilogue + the boundary kernel
+step0 = torch.full_like(u, 0.01)
+uh = u.clone()
+draws = torch.empty((10, db.P, N * G), device='cuda')
+db.hmc_run(uh, step0, 3, 0, 0, 15, 0.75, seed=1, draws=draws)
+torch.cuda.synchronize()
+e0.record()
+db.hmc_run(uh, step0, 10, 0, 0, 15, 0.75, seed=2, draws=draws)
+e1.record(); torch.cuda.synchronize()
+print('%%s eval %%.4f ms  hmc transition %%.3f ms  lp_sum=%%.6e grad_abs=%%.6e' %% (os.path.basename(sys.argv[1]), ms_eval,
+      e0.elapsed_time(e1) / 10, float(lp.double().sum()), float(gr.double().abs().sum())))
 ''' % ROOT
 it = sys.argv[1] if len(sys.argv) > 1 else '30'
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 2

@@ -118,6 +118,10 @@ __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ gra
   if (b < B) leap_epilogue(lf, P, B, b, grad);
 }
 
+// 96 registers is the ceiling for 17 resident warps per SM: each of the 4 SM sub-partitions owns 16 K
+// registers and one of them must host 5 of the 17 warps (5 x 32 x 104 > 16384).  Measured with
+// __maxnreg__: 104 / 112 / 120 registers -> 1.26 / 1.15 / 1.11 ms (second wave) against 0.87 ms at 96
+// (unconstrained, ptxas would take 192).
 template <int S, bool STAGED, bool EFF>
 __global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 20 : 8))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,

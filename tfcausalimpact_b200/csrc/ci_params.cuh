@@ -13,6 +13,10 @@
 #pragma once
 #include "ci_core.cuh"
 
+#ifndef CI_PB
+#define CI_PB 4   // covariates per load group in the parameter transforms
+#endif
+
 namespace ci {
 
 // Per-series constants, struct-of-arrays on the device: sconst[field * N + n].
@@ -62,16 +66,35 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
     const float* ulsv = u + 4 * ld;
     const float* ulsn = u + (long)(4 + k) * ld;
     const float* uwn = u + (long)(4 + 2 * k) * ld;
-    // the loads of covariate j+1 are in flight while covariate j is processed
-    float a = ulsv[0], b = ulsn[0], wn = uwn[0];
-    for (int j = 0; j < k; ++j) {
-      const int jn = (j + 1 < k) ? j + 1 : j;
-      const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
-      const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(b);
-      const float lsv = pa.sp, lsn = pb.sp;
-      lp += -1.5f * logf(lsv) - 0.5f * rcp(lsv) - 0.5f * lsn * lsn - 0.5f * wn * wn + pa.lsig + pb.lsig;
-      beta[(long)j * ldb] = wn * lsn * sqrtf(lsv) * G;
-      a = an; b = bn; wn = wnn;
+    // covariates in groups of CI_PB: the 3 CI_PB loads of the next group are in flight while the current
+    // group is processed, so the (DRAM) latency of the parameter columns is paid k / CI_PB times, not k times
+    float a[CI_PB], b[CI_PB], wn[CI_PB];
+#pragma unroll
+    for (int q = 0; q < CI_PB; ++q) {
+      const long o = (long)(q < k ? q : k - 1) * ld;
+      a[q] = ulsv[o]; b[q] = ulsn[o]; wn[q] = uwn[o];
+    }
+    for (int j0 = 0; j0 < k; j0 += CI_PB) {
+      float an[CI_PB], bn[CI_PB], wnn[CI_PB];
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        const int jn = j0 + CI_PB + q;
+        const long o = (long)(jn < k ? jn : k - 1) * ld;
+        an[q] = ulsv[o]; bn[q] = ulsn[o]; wnn[q] = uwn[o];
+      }
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        if (j0 + q < k) {
+          const SoftplusPack pa = softplus_pack(a[q]), pb = softplus_pack(b[q]);
+          const float lsv = pa.sp, lsn = pb.sp;
+          lp += -1.5f * logf(lsv) - 0.5f * rcp(lsv) - 0.5f * lsn * lsn - 0.5f * wn[q] * wn[q] + pa.lsig + pb.lsig;
+          beta[(long)(j0 + q) * ldb] = wn[q] * lsn * sqrtf(lsv) * G;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        a[q] = an[q]; b[q] = bn[q]; wn[q] = wnn[q];
+      }
     }
   }
   if (S > 1) {
@@ -122,23 +145,42 @@ CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int
     float* glsn = grad + (long)(4 + k) * ld;
     float* gwn = grad + (long)(4 + 2 * k) * ld;
     float dG = 0.f;
-    float a = ulsv[0], b = ulsn[0], wn = uwn[0], bb = beta_bar[0];
-    for (int j = 0; j < k; ++j) {
-      const int jn = (j + 1 < k) ? j + 1 : j;
-      const float an = ulsv[(long)jn * ld], bn = ulsn[(long)jn * ld], wnn = uwn[(long)jn * ld];
-      const float bbn = beta_bar[(long)jn * ldb];
-      const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(b);
-      const float lsv = pa.sp, lsn = pb.sp;
-      const float sq = sqrtf(lsv);
-      const float ilsv = rcp(lsv);
-      const float l = lsn * sq;
-      dG = fmaf(bb, wn * l, dG);
-      gwn[(long)j * ld] = bb * l * G - wn;
-      const float dl = bb * wn * G;
-      glsn[(long)j * ld] = (dl * sq - lsn) * pb.sig + pb.nsig;
-      // d sqrt(v)/dv = sqrt(v) / (2 v);  d log IG(.5,.5)/dv = -1.5 / v + 0.5 / v^2
-      glsv[(long)j * ld] = (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig;
-      a = an; b = bn; wn = wnn; bb = bbn;
+    float a[CI_PB], b[CI_PB], wn[CI_PB];
+#pragma unroll
+    for (int q = 0; q < CI_PB; ++q) {
+      const long o = (long)(q < k ? q : k - 1) * ld;
+      a[q] = ulsv[o]; b[q] = ulsn[o]; wn[q] = uwn[o];
+    }
+    for (int j0 = 0; j0 < k; j0 += CI_PB) {
+      float an[CI_PB], bn[CI_PB], wnn[CI_PB];
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        const int jn = j0 + CI_PB + q;
+        const long o = (long)(jn < k ? jn : k - 1) * ld;
+        an[q] = ulsv[o]; bn[q] = ulsn[o]; wnn[q] = uwn[o];
+      }
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        const int j = j0 + q;
+        if (j < k) {
+          const float bb = beta_bar[(long)j * ldb];
+          const SoftplusPack pa = softplus_pack(a[q]), pb = softplus_pack(b[q]);
+          const float lsv = pa.sp, lsn = pb.sp;
+          const float sq = sqrtf(lsv);
+          const float ilsv = rcp(lsv);
+          const float l = lsn * sq;
+          dG = fmaf(bb, wn[q] * l, dG);
+          gwn[(long)j * ld] = bb * l * G - wn[q];
+          const float dl = bb * wn[q] * G;
+          glsn[(long)j * ld] = (dl * sq - lsn) * pb.sig + pb.nsig;
+          // d sqrt(v)/dv = sqrt(v) / (2 v);  d log IG(.5,.5)/dv = -1.5 / v + 0.5 / v^2
+          glsv[(long)j * ld] = (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CI_PB; ++q) {
+        a[q] = an[q]; b[q] = bn[q]; wn[q] = wnn[q];
+      }
     }
     grad[3 * ld] = (dG * sq_gsv * CI_WEIGHTS_PRIOR_SCALE - gsn) * pn.sig + pn.nsig;
     grad[2 * ld] = (dG * gsn * CI_WEIGHTS_PRIOR_SCALE * 0.5f / sq_gsv - 1.5f / gsv + 0.5f / (gsv * gsv)) * pg.sig +
