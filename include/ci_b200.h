@@ -186,7 +186,9 @@ int ci_reduce_summary(const ci_layout* L, const float* d_y_post, const float* d_
  * Replaces: tfp.sts.decompose_by_component / decompose_forecast_by_component as the reference's
  * notebook applies them to ci.model / ci.model_samples (notebooks/getting_started.ipynb:125,144).
  * L->G = posterior draws per series.  Outputs are mixtures over the draws, in MODEL units:
- *   d_comp_mean, d_comp_sd  [3][N][W]   components: 0 LocalLevel, 1 regression (X_t beta), 2 Seasonal
+ *   d_comp_mean, d_comp_sd  [C][N][W]   components: 0 trend (LocalLevel / LocalLinearTrend level),
+ *                                       1 regression (X_t beta), 2 Seasonal, 3 second Seasonal (C = 4 only
+ *                                       when L->S2 > 1, else C = 3)
  *   W = T (smoothed pre-period marginals) or Tf (forecast marginals); absent components are zero. */
 size_t ci_decompose_workspace_bytes(const ci_layout* L);
 int ci_decompose_by_component(const ci_layout* L, const ci_data* D, const float* d_u, float* d_comp_mean,

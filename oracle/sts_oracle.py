@@ -867,12 +867,17 @@ def smooth_components(prob: Problem, u_draws: torch.Tensor, series: torch.Tensor
         Ps[t] = Pf[t] + J @ (Ps[t + 1] - Pp[t + 1]) @ J.transpose(1, 2)
     ms = torch.stack(ms, 1)                                     # [B, T, d]
     Ps = torch.stack(Ps, 1)                                     # [B, T, d, d]
-    out = {'LocalLevel': _mixture_moments(ms[:, :, 0], Ps[:, :, 0, 0], G)}
+    out = {'LocalLevel': _mixture_moments(ms[:, :, 0], Ps[:, :, 0, 0], G)}   # trend: the level entry
     if L.k > 0:
         reg = off - prob.st.mean[series][:, None]
         out['SparseLinearRegression'] = _mixture_moments(reg, torch.zeros_like(reg), G)
+    # a Seasonal component contributes its current effect = first residual of its block (H picks it)
     if L.S > 1:
-        out['Seasonal'] = _mixture_moments(ms[:, :, 1], Ps[:, :, 1, 1], G)
+        i1 = L.nt
+        out['Seasonal'] = _mixture_moments(ms[:, :, i1], Ps[:, :, i1, i1], G)
+    if L.S2 > 1:
+        i2 = L.nt + L.S - 1
+        out['Seasonal2'] = _mixture_moments(ms[:, :, i2], Ps[:, :, i2, i2], G)
     return out
 
 
@@ -881,11 +886,14 @@ def forecast_components(prob: Problem, u_draws: torch.Tensor, series: torch.Tens
     L = prob.L
     _, _, m, P, th, ssm = one_step_predictive(prob, u_draws, series)
     off = residuals(prob, th, series, L.T, L.T + L.Tf)
-    lm, lv, sm, sv = [], [], [], []
+    lm, lv, sm, sv, sm2, sv2 = [], [], [], [], [], []
+    i1, i2 = L.nt, L.nt + L.S - 1
     for t in range(L.Tf):
         lm.append(m[:, 0]); lv.append(P[:, 0, 0])
         if L.S > 1:
-            sm.append(m[:, 1]); sv.append(P[:, 1, 1])
+            sm.append(m[:, i1]); sv.append(P[:, i1, i1])
+        if L.S2 > 1:
+            sm2.append(m[:, i2]); sv2.append(P[:, i2, i2])
         Ft = ssm.F(L.T + t)
         m = m @ Ft.T
         P = Ft[None] @ P @ Ft.T[None] + ssm.Q(L.T + t)
@@ -895,4 +903,6 @@ def forecast_components(prob: Problem, u_draws: torch.Tensor, series: torch.Tens
         out['SparseLinearRegression'] = _mixture_moments(reg, torch.zeros_like(reg), G)
     if L.S > 1:
         out['Seasonal'] = _mixture_moments(torch.stack(sm, 1), torch.stack(sv, 1), G)
+    if L.S2 > 1:
+        out['Seasonal2'] = _mixture_moments(torch.stack(sm2, 1), torch.stack(sv2, 1), G)
     return out

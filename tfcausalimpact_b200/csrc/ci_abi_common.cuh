@@ -75,6 +75,11 @@ int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, floa
                     float* tape, cudaStream_t stream);
 int launch_filter_big(const ci_layout* L, const ci_data* D, const float* d_u, float* pm, float* pv, float* fs,
                       cudaStream_t stream);
+size_t big_hist_floats(const ci_layout* L);     // smoother history [B][T][3 D + 5]
+int launch_smooth_big(const ci_layout* L, const ci_data* D, const float* d_u, float* hist, float* cmean, float* cvar,
+                      cudaStream_t stream);
+int launch_forecast_moments_big(const ci_layout* L, const float* fs, const float* scal, float* cmean, float* cvar,
+                                cudaStream_t stream);
 void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
                          const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t stream);
 

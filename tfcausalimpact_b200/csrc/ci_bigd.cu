@@ -571,6 +571,250 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
   }
 }
 
+// ---- component decomposition on the warp-per-lane path (ci_decompose.cu dispatches here) ---------------
+// Smoother in the Durbin-Koopman backward form, which needs no per-step matrix inverse and only the
+// columns of the PREDICTED covariance that belong to the observed entries:
+//     r_{t-1} = H v/s + L^T r_t,   N_{t-1} = H H^T / s + L^T N_t L,   L = F (I - K H^T),  K = P H / s
+//     E[x_t | y]   = m_t + P_t r_{t-1},   Var[x_t | y] = P_t - P_t N_{t-1} P_t
+// The forward pass keeps, per step, the columns P_t[:, c] and means m_t[c] for c in {level, current season
+// (, current season of the second component)} plus (v, 1/s): hist[B][T][3 D + 5].  N lives in shared memory
+// (it re-uses the covariance buffer); L^T N L touches only the rows/columns of H, like the adjoint above.
+__host__ __device__ __forceinline__ int big_hist_width(const ci_layout& L) { return 3 * big_D(L) + 5; }
+
+template <int NC, bool TWO>
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+k_smooth_big(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+             float* __restrict__ hist, float* __restrict__ cmean, float* __restrict__ cvar) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = L.S, so = big_nt(L), so2 = big_so2(L), S2 = TWO ? L.S2 : 1, D = big_D(L), k = L.k, T = L.T;
+  const int HW = big_hist_width(L);
+  const long B = (long)L.N * L.G;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long b = (long)blockIdx.x * BIG_WARPS + w;
+  if (b >= B) return;
+  const int n = (int)(b / L.G);
+  const int per_warp = D * D + 8 * D + (k > 0 ? k : 1) + 8;
+  float* P = smem + (long)w * per_warp;     // covariance (forward), then N (backward)
+  float* m = P + D * D;
+  float* g = m + D;                         // g (forward) / K (backward)
+  float* rv = g + D;
+  float* pc0 = rv + D;
+  float* pcJ = pc0 + D;
+  float* pc2 = pcJ + D;
+  float* beta = pc2 + 3 * D;
+  float* scal = beta + (k > 0 ? k : 1);
+  if (lane == 0) {
+    if (!big_gen(L)) {
+      const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = 0.f; scal[5] = 0.f;
+    } else {
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, L.S2);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[4] = ls.qs; scal[5] = ls.qd2;
+    }
+  }
+  __syncwarp();
+  const float R = scal[0], ql = scal[1], qd = scal[2], qs = scal[4], qd2 = scal[5];
+  big_init(P, m, D, S, so, S2, sconst[SC_M0 * L.N + n], sconst[SC_P0 * L.N + n], sconst[SC_SD * L.N + n], lane);
+  const Cols<NC> cl(lane, D);
+  float* hb = hist + b * (long)T * HW;
+  for (int t = 0; t < T; ++t) {
+    const BigSeason z = big_season<TWO>(L, so, so2, t);
+    float* he = hb + (long)t * HW;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      if (cl.ok[q]) {
+        const int j = cl.j[q];
+        he[j] = P[j * D];
+        he[D + j] = S > 1 ? P[j * D + z.J] : 0.f;
+        he[2 * D + j] = TWO ? P[j * D + z.J2] : 0.f;
+      }
+    }
+    if (lane == 0) {
+      he[3 * D] = m[0];
+      he[3 * D + 1] = S > 1 ? m[z.J] : 0.f;
+      he[3 * D + 2] = TWO ? m[z.J2] : 0.f;
+    }
+    const float resid = big_resid(XY, L, n, t, beta, lane);
+    float s, v, is;
+    const bool obs = big_step<NC, 8, TWO>(P, m, g, D, S, so, S2, so2, z, resid, R, ql, qs, qd, qd2, s, v, is, lane);
+    if (lane == 0) {
+      he[3 * D + 3] = obs ? v : __int_as_float(0x7fc00000);
+      he[3 * D + 4] = is;
+    }
+    __syncwarp();
+  }
+  // ---- backward recursion --------------------------------------------------------------------------
+  float* Nm = P;
+  for (int i = lane; i < D * D; i += 32) Nm[i] = 0.f;
+  for (int j = lane; j < D; j += 32) rv[j] = 0.f;
+  __syncwarp();
+  for (int t = T - 1; t >= 0; --t) {
+    const BigSeason z = big_season<TWO>(L, so, so2, t);
+    const int J = z.J, J2 = z.J2;
+    const float* he = hb + (long)t * HW;
+    float p0[NC], pJ[NC], p2[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      p0[q] = cl.ok[q] ? he[cl.j[q]] : 0.f;
+      pJ[q] = cl.ok[q] ? he[D + cl.j[q]] : 0.f;
+      p2[q] = cl.ok[q] ? he[2 * D + cl.j[q]] : 0.f;
+      if (cl.ok[q]) {
+        pc0[cl.j[q]] = p0[q];
+        pcJ[cl.j[q]] = pJ[q];
+        pc2[cl.j[q]] = p2[q];
+      }
+    }
+    const float m0 = he[3 * D], mJ = he[3 * D + 1], m2 = he[3 * D + 2];
+    const float v = he[3 * D + 3], is = he[3 * D + 4];
+    const bool obs = (v == v);
+    if (so == 2) {   // r <- F^T r,  N <- F^T N F   (LocalLinearTrend transition)
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+        if (cl.ok[q]) Nm[D + cl.j[q]] += Nm[cl.j[q]];            // row 1 += row 0
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NC; ++q)
+        if (cl.ok[q]) Nm[cl.j[q] * D + 1] += Nm[cl.j[q] * D];    // column 1 += column 0
+      if (lane == 0) rv[1] += rv[0];
+    }
+    __syncwarp();
+    if (obs) {
+      float Kj[NC], aj[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        Kj[q] = (p0[q] + pJ[q] + p2[q]) * is;
+        aj[q] = 0.f;
+        if (cl.ok[q]) g[cl.j[q]] = Kj[q];
+      }
+      __syncwarp();
+#pragma unroll 4
+      for (int i = 0; i < D; ++i) {
+        const float ki = g[i];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) aj[q] = fmaf(Nm[i * D + cl.j[q]], ki, aj[q]);
+      }
+      float pk = 0.f, pr = 0.f;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        if (cl.ok[q]) {
+          pk = fmaf(Kj[q], aj[q], pk);
+          pr = fmaf(Kj[q], rv[cl.j[q]], pr);
+        }
+      }
+      const float wgt = warp_sum(pk) + is;
+      const float dr = v * is - warp_sum(pr);
+      __syncwarp();
+      // N <- N - H a^T - a H^T + wgt H H^T : rows of H, then columns of H, then the H x H block
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        if (cl.ok[q]) {
+          Nm[cl.j[q]] -= aj[q];
+          if (S > 1) Nm[J * D + cl.j[q]] -= aj[q];
+          if (TWO) Nm[J2 * D + cl.j[q]] -= aj[q];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        if (cl.ok[q]) {
+          Nm[cl.j[q] * D] -= aj[q];
+          if (S > 1) Nm[cl.j[q] * D + J] -= aj[q];
+          if (TWO) Nm[cl.j[q] * D + J2] -= aj[q];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        int hs[3] = {0, J, J2};
+        const int nh = 1 + (S > 1 ? 1 : 0) + (TWO ? 1 : 0);
+        for (int c1 = 0; c1 < nh; ++c1)
+          for (int c2 = 0; c2 < nh; ++c2) Nm[hs[c1] * D + hs[c2]] += wgt;
+        for (int c1 = 0; c1 < nh; ++c1) rv[hs[c1]] += dr;
+      }
+      __syncwarp();
+    }
+    // smoothed marginals of the observed entries: mean = m_c + p_c . r,  var = p_c[c] - p_c^T N p_c
+    float q0[NC], qJ[NC], q2[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) q0[q] = qJ[q] = q2[q] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < D; ++i) {
+      const float a0 = pc0[i], aJ = pcJ[i], a2 = pc2[i];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        const float nv = Nm[i * D + cl.j[q]];
+        q0[q] = fmaf(nv, a0, q0[q]);
+        qJ[q] = fmaf(nv, aJ, qJ[q]);
+        if (TWO) q2[q] = fmaf(nv, a2, q2[q]);
+      }
+    }
+    float e0 = 0.f, eJ = 0.f, e2 = 0.f, f0 = 0.f, fJ = 0.f, f2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      if (cl.ok[q]) {
+        const float rj = rv[cl.j[q]];
+        e0 = fmaf(p0[q], rj, e0); eJ = fmaf(pJ[q], rj, eJ); e2 = fmaf(p2[q], rj, e2);
+        f0 = fmaf(p0[q], q0[q], f0); fJ = fmaf(pJ[q], qJ[q], fJ); f2 = fmaf(p2[q], q2[q], f2);
+      }
+    }
+    e0 = warp_sum(e0); eJ = warp_sum(eJ); e2 = warp_sum(e2);
+    f0 = warp_sum(f0); fJ = warp_sum(fJ); f2 = warp_sum(f2);
+    if (lane == 0) {
+      cmean[((long)0 * T + t) * B + b] = m0 + e0;
+      cvar[((long)0 * T + t) * B + b] = fmaxf(pc0[0] - f0, 0.f);
+      cmean[((long)1 * T + t) * B + b] = S > 1 ? mJ + eJ : 0.f;
+      cvar[((long)1 * T + t) * B + b] = S > 1 ? fmaxf(pcJ[J] - fJ, 0.f) : 0.f;
+      cmean[((long)2 * T + t) * B + b] = TWO ? m2 + e2 : 0.f;
+      cvar[((long)2 * T + t) * B + b] = TWO ? fmaxf(pc2[J2] - f2, 0.f) : 0.f;
+    }
+    __syncwarp();
+  }
+}
+
+// Component moments over the forecast horizon: prior propagation from the forecast state (m, P).
+template <int NC, bool TWO>
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+k_forecast_moments_big(ci_layout L, const float* __restrict__ fstate, const float* __restrict__ scal_g,
+                       float* __restrict__ cmean, float* __restrict__ cvar) {
+  extern __shared__ __align__(16) float smem[];
+  const int S = L.S, so = big_nt(L), so2 = big_so2(L), S2 = TWO ? L.S2 : 1, D = big_D(L), Tf = L.Tf;
+  const long B = (long)L.N * L.G;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long b = (long)blockIdx.x * BIG_WARPS + w;
+  if (b >= B) return;
+  const int per_warp = D * D + 8 * D + (L.k > 0 ? L.k : 1) + 8;
+  float* P = smem + (long)w * per_warp;
+  float* m = P + D * D;
+  float* g = m + D;
+  const float* fs = fstate + b * (long)(D + 2 * D * D);
+  for (int j = lane; j < D; j += 32) m[j] = fs[j];
+  for (int i = lane; i < D * D; i += 32) P[i] = fs[D + i];
+  __syncwarp();
+  const float R = scal_g[0 * B + b], ql = scal_g[1 * B + b], qd = scal_g[2 * B + b], qs = scal_g[4 * B + b],
+              qd2 = scal_g[5 * B + b];
+  for (int t = 0; t < Tf; ++t) {
+    const BigSeason z = big_season<TWO>(L, so, so2, L.T + t);
+    if (lane == 0) {
+      cmean[((long)0 * Tf + t) * B + b] = m[0];
+      cvar[((long)0 * Tf + t) * B + b] = P[0];
+      cmean[((long)1 * Tf + t) * B + b] = S > 1 ? m[z.J] : 0.f;
+      cvar[((long)1 * Tf + t) * B + b] = S > 1 ? P[z.J * D + z.J] : 0.f;
+      cmean[((long)2 * Tf + t) * B + b] = TWO ? m[z.J2] : 0.f;
+      cvar[((long)2 * Tf + t) * B + b] = TWO ? P[z.J2 * D + z.J2] : 0.f;
+    }
+    __syncwarp();
+    float s, v, is;
+    big_step<NC, 8, TWO>(P, m, g, D, S, so, S2, so2, z, __int_as_float(0x7fc00000), R, ql, qs, qd, qd2, s, v, is, lane);
+  }
+}
+
+size_t big_smooth_smem_bytes(const ci_layout* L) {
+  const int D = big_D(*L);
+  return (size_t)BIG_WARPS * (D * D + 8 * D + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
+}
+size_t big_hist_floats(const ci_layout* L) {
+  return (size_t)L->N * L->G * L->T * big_hist_width(*L);
+}
+
 size_t big_smem_bytes(const ci_layout* L) {
   const int D = big_D(*L);
   return (size_t)BIG_WARPS * (2 * D * D + 4 * D + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
@@ -651,6 +895,50 @@ void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal,
   k_forecast_mean_big<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(*L, fs, off, pm);
   if (sims)
     k_forecast_sample_big<<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(*L, nsamp, seed, fs, scal, off, mu_sig, sims);
+}
+
+int launch_smooth_big(const ci_layout* L, const ci_data* D, const float* d_u, float* hist, float* cmean, float* cvar,
+                      cudaStream_t st) {
+  if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  const size_t smem = big_smooth_smem_bytes(L);
+  const long B = (long)L->N * L->G;
+  const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
+  const int Dl = big_D(*L);
+#define CI_BIG_SMOOTH(NC)                                                                                    \
+  {                                                                                                          \
+    if (L->S2 > 1) {                                                                                         \
+      if (int e = big_attr(k_smooth_big<NC, true>, smem)) return e;                                          \
+      k_smooth_big<NC, true><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, hist, cmean, cvar);  \
+    } else {                                                                                                 \
+      if (int e = big_attr(k_smooth_big<NC, false>, smem)) return e;                                         \
+      k_smooth_big<NC, false><<<grid, BIG_WARPS * 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, hist, cmean, cvar); \
+    }                                                                                                        \
+  }
+  if (Dl <= 32) CI_BIG_SMOOTH(1) else if (Dl <= 64) CI_BIG_SMOOTH(2) else CI_BIG_SMOOTH(3)
+#undef CI_BIG_SMOOTH
+  return CI_OK;
+}
+
+int launch_forecast_moments_big(const ci_layout* L, const float* fs, const float* scal, float* cmean, float* cvar,
+                                cudaStream_t st) {
+  if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  const size_t smem = big_smooth_smem_bytes(L);
+  const long B = (long)L->N * L->G;
+  const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
+  const int Dl = big_D(*L);
+#define CI_BIG_FMOM(NC)                                                                                  \
+  {                                                                                                      \
+    if (L->S2 > 1) {                                                                                     \
+      if (int e = big_attr(k_forecast_moments_big<NC, true>, smem)) return e;                            \
+      k_forecast_moments_big<NC, true><<<grid, BIG_WARPS * 32, smem, st>>>(*L, fs, scal, cmean, cvar);     \
+    } else {                                                                                             \
+      if (int e = big_attr(k_forecast_moments_big<NC, false>, smem)) return e;                           \
+      k_forecast_moments_big<NC, false><<<grid, BIG_WARPS * 32, smem, st>>>(*L, fs, scal, cmean, cvar);    \
+    }                                                                                                    \
+  }
+  if (Dl <= 32) CI_BIG_FMOM(1) else if (Dl <= 64) CI_BIG_FMOM(2) else CI_BIG_FMOM(3)
+#undef CI_BIG_FMOM
+  return CI_OK;
 }
 
 }  // namespace ci

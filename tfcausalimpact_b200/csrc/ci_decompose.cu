@@ -10,6 +10,9 @@
 //                        per draw lane; emits level / seasonal mean and variance per step
 //   k_forecast_moments<S> prior propagation of (m, P) from the forecast state over Tf steps
 //   k_mix_components      mixture over the G draws of a series: mean, sqrt(E[var + mean^2] - mean^2)
+// Layouts outside the register-resident set (large nseasons, LocalLinearTrend, dense regression, a second
+// Seasonal component) are served by the warp-per-lane kernels k_smooth_big / k_forecast_moments_big
+// (ci_bigd.cu, Durbin-Koopman backward recursion); outputs then carry a 4th row when S2 > 1.
 // Not a hot path (lanes = posterior draws, run once per fit): arithmetic is dense and rolled.
 #include "ci_abi_common.cuh"
 #include "ci_kalman.cuh"
@@ -182,14 +185,15 @@ __global__ void k_forecast_moments(int N, int G, int T, int Tf, int r, const flo
   }
 }
 
-// out_mean / out_sd [3][N][W] (level, regression, seasonal) from per-draw moments [2][W][B] and the
-// per-draw offsets [W][B] (regression component = offset - mean(y), deterministic per draw).
-__global__ void k_mix_components(int N, int G, int W, int has_reg, const float* __restrict__ cmean,
+// out_mean / out_sd [ncomp][N][W] (level, regression, seasonal[, second seasonal]) from per-draw moments
+// [ncomp - 1][W][B] and the per-draw offsets [W][B] (regression component = offset - mean(y),
+// deterministic per draw).
+__global__ void k_mix_components(int N, int G, int W, int has_reg, int ncomp, const float* __restrict__ cmean,
                                  const float* __restrict__ cvar, const float* __restrict__ off,
                                  const float* __restrict__ sconst, float* __restrict__ out_mean,
                                  float* __restrict__ out_sd) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)3 * N * W) return;
+  if (idx >= (long)ncomp * N * W) return;
   const int t = (int)(idx % W);
   const int n = (int)((idx / W) % N);
   const int comp = (int)(idx / ((long)N * W));     // 0 level, 1 regression, 2 seasonal
@@ -202,7 +206,7 @@ __global__ void k_mix_components(int N, int G, int W, int has_reg, const float* 
       m = has_reg ? off[(long)t * B + b] - sconst[SC_MEAN * N + n] : 0.f;
       v = 0.f;
     } else {
-      const int c = comp == 0 ? 0 : 1;
+      const int c = comp == 0 ? 0 : comp - 1;
       m = cmean[((long)c * W + t) * B + b];
       v = cvar[((long)c * W + t) * B + b];
     }
@@ -219,14 +223,16 @@ struct DecWs {
   float* beta;   // [max(k,1)][B]
   float* scal;   // [8][B]
   float* off;    // [W][B]
-  float* cmean;  // [2][W][B]
-  float* cvar;   // [2][W][B]
-  float* hist;   // [T][2][S+NP][B]   (smoothing only)
+  float* cmean;  // [2][W][B]  (warp-per-lane path: [3][W][B] = level, seasonal, second seasonal)
+  float* cvar;   // same shape
+  float* hist;   // [T][2][S+NP][B]   (smoothing only; warp-per-lane path: [B][T][3 D + 5])
 };
 static size_t dec_ws_floats(const ci_layout* L, int W, bool smooth, DecWs* ws, Carver* c) {
   const size_t B = (size_t)L->N * L->G;
-  const size_t nb = (size_t)(L->k > 0 ? L->k : 1) * B, ns = 8 * B, no = (size_t)W * B, nc = 2 * (size_t)W * B;
-  const size_t S = L->S, nh = smooth ? (size_t)L->T * 2 * (S + S * (S + 1) / 2) * B : 0;
+  const bool reg = ci_reg_path(L);
+  const size_t nb = (size_t)(L->k > 0 ? L->k : 1) * B, ns = 8 * B, no = (size_t)W * B, nc = (reg ? 2 : 3) * (size_t)W * B;
+  const size_t S = L->S;
+  const size_t nh = !smooth ? 0 : (reg ? (size_t)L->T * 2 * (S + S * (S + 1) / 2) * B : big_hist_floats(L));
   if (ws && c) {
     ws->beta = c->floats(nb);
     ws->scal = c->floats(ns);
@@ -259,7 +265,7 @@ using namespace ci;
 extern "C" {
 
 size_t ci_decompose_workspace_bytes(const ci_layout* L) {
-  if (check_layout(L) || !ci_reg_path(L)) return 0;
+  if (check_layout(L) || (!ci_reg_path(L) && !big_supported(L))) return 0;
   const size_t a = dec_ws_floats(L, L->T, true, nullptr, nullptr);
   const size_t b = dec_ws_floats(L, L->Tf > 0 ? L->Tf : 1, false, nullptr, nullptr);
   return a > b ? a : b;
@@ -270,7 +276,8 @@ int ci_decompose_by_component(const ci_layout* L, const ci_data* D, const float*
   if (int e = check_layout(L)) return e;
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_comp_mean && d_comp_sd && d_workspace, "NULL pointer");
-  if (!ci_reg_path(L)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
+  if (!ci_reg_path(L) && !big_supported(L))
+    return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
   if (workspace_bytes < dec_ws_floats(L, L->T, true, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", dec_ws_floats(L, L->T, true, nullptr, nullptr));
   cudaStream_t st = (cudaStream_t)stream;
@@ -279,9 +286,14 @@ int ci_decompose_by_component(const ci_layout* L, const ci_data* D, const float*
   dec_ws_floats(L, L->T, true, &ws, &c);
   launch_params_forward(L, D, d_u, ws.beta, ws.scal, st);
   launch_offsets(L, D, ws.beta, ws.off, 0, L->T, 0, st);
-  CI_DISPATCH_S(L->S, (launch_smooth<S_>(L, D, ws, st)));
-  const long tot = 3L * L->N * L->T;
-  k_mix_components<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L->N, L->G, L->T, L->k > 0, ws.cmean, ws.cvar, ws.off,
+  const int ncomp = 3 + (L->S2 > 1 ? 1 : 0);
+  if (ci_reg_path(L)) {
+    CI_DISPATCH_S(L->S, (launch_smooth<S_>(L, D, ws, st)));
+  } else {
+    if (int e = launch_smooth_big(L, D, d_u, ws.hist, ws.cmean, ws.cvar, st)) return e;
+  }
+  const long tot = (long)ncomp * L->N * L->T;
+  k_mix_components<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L->N, L->G, L->T, L->k > 0, ncomp, ws.cmean, ws.cvar, ws.off,
                                                                   D->d_sconst, d_comp_mean, d_comp_sd);
   CI_CHECK_LAUNCH();
   return CI_OK;
@@ -294,7 +306,8 @@ int ci_decompose_forecast(const ci_layout* L, const ci_data* D, const float* d_u
   CI_CHECK_ARG(D && D->d_y && D->d_sconst && D->d_X, "NULL data pointer");
   CI_CHECK_ARG(d_u && d_fstate && d_comp_mean && d_comp_sd && d_workspace, "NULL pointer");
   CI_CHECK_ARG(L->Tf >= 1, "forecast horizon Tf must be >= 1");
-  if (!ci_reg_path(L)) return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
+  if (!ci_reg_path(L) && !big_supported(L))
+    return fail(CI_ERR_UNSUPPORTED, "decomposition: nseasons=%d not supported", L->S);
   if (workspace_bytes < dec_ws_floats(L, L->Tf, false, nullptr, nullptr))
     return fail(CI_ERR_WORKSPACE_TOO_SMALL, "workspace needs %zu bytes", dec_ws_floats(L, L->Tf, false, nullptr, nullptr));
   cudaStream_t st = (cudaStream_t)stream;
@@ -303,9 +316,14 @@ int ci_decompose_forecast(const ci_layout* L, const ci_data* D, const float* d_u
   dec_ws_floats(L, L->Tf, false, &ws, &c);
   launch_params_forward(L, D, d_u, ws.beta, ws.scal, st);
   launch_offsets(L, D, ws.beta, ws.off, L->T, L->T + L->Tf, 0, st);
-  CI_DISPATCH_S(L->S, (launch_fmom<S_>(L, d_fstate, ws, st)));
-  const long tot = 3L * L->N * L->Tf;
-  k_mix_components<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L->N, L->G, L->Tf, L->k > 0, ws.cmean, ws.cvar, ws.off,
+  const int ncomp = 3 + (L->S2 > 1 ? 1 : 0);
+  if (ci_reg_path(L)) {
+    CI_DISPATCH_S(L->S, (launch_fmom<S_>(L, d_fstate, ws, st)));
+  } else {
+    if (int e = launch_forecast_moments_big(L, d_fstate, ws.scal, ws.cmean, ws.cvar, st)) return e;
+  }
+  const long tot = (long)ncomp * L->N * L->Tf;
+  k_mix_components<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(L->N, L->G, L->Tf, L->k > 0, ncomp, ws.cmean, ws.cvar, ws.off,
                                                                   D->d_sconst, d_comp_mean, d_comp_sd);
   CI_CHECK_LAUNCH();
   return CI_OK;

@@ -23,9 +23,14 @@ class ComponentDist:
 
 def _components(model, mean, sd):
     out = OrderedDict()
+    seasonal_row = 2
     for comp in model.components:
-        row = {cimodel.LocalLevel: 0, cimodel.LocalLinearTrend: 0, cimodel.SparseLinearRegression: 1,
-               cimodel.LinearRegression: 1, cimodel.Seasonal: 2}[type(comp)]
+        if isinstance(comp, cimodel.Seasonal):
+            row = seasonal_row          # first Seasonal -> row 2, second -> row 3
+            seasonal_row += 1
+        else:
+            row = {cimodel.LocalLevel: 0, cimodel.LocalLinearTrend: 0, cimodel.SparseLinearRegression: 1,
+                   cimodel.LinearRegression: 1}[type(comp)]
         out[comp] = ComponentDist(mean[row, 0], sd[row, 0])
     return out
 

@@ -190,12 +190,14 @@ class DeviceBatch:
 
     # ---- component decomposition -------------------------------------------------------------
     def decompose(self, u, fstate=None):
-        """Mixture-over-draws component marginals [3, N, W] (mean, sd): smoothed over the observed
-        period (fstate=None, W = T) or forecast over the horizon (fstate given, W = Tf)."""
+        """Mixture-over-draws component marginals [C, N, W] (mean, sd): smoothed over the observed
+        period (fstate=None, W = T) or forecast over the horizon (fstate given, W = Tf).
+        Rows: trend, regression, seasonal (, second seasonal: C = 4 when the model has one, else 3)."""
         B = u.shape[1]
         L = self.layout(B // self.N)
         W = self.T if fstate is None else self.Tf
-        mean, sd = self._f32(3, self.N, W), self._f32(3, self.N, W)
+        C = 4 if self.S2 > 1 else 3
+        mean, sd = self._f32(C, self.N, W), self._f32(C, self.N, W)
         nbytes = self.lib.ci_decompose_workspace_bytes(ctypes.byref(L))
         if nbytes == 0:
             raise nt.NativeError(f'component decomposition does not support nseasons={self.S}')
