@@ -26,7 +26,10 @@ CASES = [
     (8, 1, 2, 60, 0.0, 3, 2),
     (9, 2, 0, 75, 0.1, 2, 3),
     (10, 3, 40, 90, 0.05, 2, 2),
-    (52, 1, 3, 130, 0.0, 2, 2),   # configs[4] latent size
+    (52, 1, 3, 130, 0.0, 2, 2),   # configs[4] latent size (few lanes -> CTA-per-lane kernel)
+    # the same large-latent layouts with enough lanes (B > 296) to stay on the warp-per-lane kernel
+    (9, 2, 2, 40, 0.1, 40, 8),
+    (52, 1, 0, 60, 0.0, 50, 6),
 ]
 
 
@@ -125,6 +128,7 @@ TWO_SEASONAL_CASES = [
     (0, 7, 1, 4, 3, 2, 60, 0.1, 2, 2),                   # default priors + a second seasonal with duration 3
     (O.FLAG_LLT | O.FLAG_OBS_LOGNORMAL, 3, 2, 5, 1, 0, 50, 0.05, 1, 3),
     (O.FLAG_OBS_LOGNORMAL | O.FLAG_LEVEL_LOGNORMAL, 12, 1, 30, 2, 1, 90, 0.0, 1, 2),
+    (O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 4, 1, 9, 1, 2, 36, 0.05, 50, 6),   # B = 300: warp-per-lane kernel
 ]
 
 

@@ -113,6 +113,38 @@ __device__ __forceinline__ BigSeason big_season(const ci_layout& L, int so, int 
   return z;
 }
 
+// Incremental form of big_season for loops over consecutive steps (no integer divisions per step).
+template <bool TWO>
+struct SeasonWalk {
+  int S, r, S2, r2, so, so2;
+  int c, ph, c2, ph2;     // season index and position inside the season, per component
+  __device__ __forceinline__ SeasonWalk(const ci_layout& L, int so_, int so2_, int t)
+      : S(L.S), r(L.r), S2(TWO ? L.S2 : 1), r2(TWO ? L.r2 : 1), so(so_), so2(so2_) {
+    c = S > 1 ? (t / r) % S : 0;
+    ph = S > 1 ? t % r : 0;
+    c2 = TWO ? (t / r2) % S2 : 0;
+    ph2 = TWO ? t % r2 : 0;
+  }
+  __device__ __forceinline__ BigSeason get() const {
+    BigSeason z;
+    z.c = c;
+    z.J = S > 1 ? so + c : 0;
+    z.change = S > 1 && ph == r - 1;
+    z.c2 = c2;
+    z.J2 = TWO ? so2 + c2 : 0;
+    z.change2 = TWO && ph2 == r2 - 1;
+    return z;
+  }
+  __device__ __forceinline__ void next() {
+    if (S > 1 && ++ph == r) { ph = 0; c = (c + 1 == S) ? 0 : c + 1; }
+    if (TWO && ++ph2 == r2) { ph2 = 0; c2 = (c2 + 1 == S2) ? 0 : c2 + 1; }
+  }
+  __device__ __forceinline__ void prev() {
+    if (S > 1 && --ph < 0) { ph = r - 1; c = (c == 0) ? S - 1 : c - 1; }
+    if (TWO && --ph2 < 0) { ph2 = r2 - 1; c2 = (c2 == 0) ? S2 - 1 : c2 - 1; }
+  }
+};
+
 template <int NC, int RB, bool TWO>
 __device__ __forceinline__ bool big_step(float* __restrict__ P, float* __restrict__ m, float* __restrict__ g, int D, int S, int so,
                                          int S2, int so2, const BigSeason z, float resid, float R, float ql, float qs,
@@ -815,6 +847,291 @@ size_t big_hist_floats(const ci_layout* L) {
   return (size_t)L->N * L->G * L->T * big_hist_width(*L);
 }
 
+// ---- CTA-per-lane evaluation: few lanes, long series (BASELINE configs[4]: 100 series x 10,000 steps) ----
+// With B << number of SMs a warp per lane leaves the machine empty and every shared-memory round trip of
+// the row sweeps is exposed.  Here one CTA of 64 x RG threads owns a lane: thread (tx, ty) holds column
+// tx of rows ty, ty + RG, ... of P and of its adjoint, so a sweep is D / RG rows deep instead of D.
+// Same arithmetic as k_eval_big (same tape layout), block barriers instead of __syncwarp.
+// The regression is hoisted out of the time loop: a parallel pre-pass writes the residuals r_t = y_t - mean -
+// X_t beta, the reverse sweep stores rbar_t, and a parallel post-pass forms beta_bar = -sum_t rbar_t X_t.
+constexpr int CTA_COLS = 64;
+
+template <int RG, bool TWO>
+__global__ void __launch_bounds__(CTA_COLS * RG)
+k_eval_cta(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+           float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, float* __restrict__ rscr) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NT = CTA_COLS * RG;
+  const int S = L.S, so = big_nt(L), so2 = big_so2(L), S2 = TWO ? L.S2 : 1, D = big_D(L), k = L.k, T = L.T;
+  const long B = (long)L.N * L.G;
+  const int tid = threadIdx.x, tx = tid & (CTA_COLS - 1), ty = tid >> 6;
+  const long b = blockIdx.x;
+  const int n = (int)(b / L.G);
+  const bool col_ok = tx < D;
+  const int kk = k > 0 ? k : 1;
+  float* P = smem;
+  float* Pb = P + D * D;
+  float* m = Pb + D * D;
+  float* g = m + D;
+  float* mb = g + D;
+  float* part = mb + D;                       // [3][RG][64] partial column sums of the reverse sweep
+  float* red = part + 3 * RG * CTA_COLS;      // [2][8] block-reduction scratch
+  float* beta = red + 16;
+  float* scal = beta + kk;
+  if (tid == 0) {
+    if (!big_gen(L)) {
+      const LaneScalars ls = params_forward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = 0.f; scal[5] = 0.f;
+    } else {
+      const GenScalars ls = params_forward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, L.S2);
+      scal[0] = ls.R; scal[1] = ls.ql; scal[2] = ls.qd; scal[3] = ls.lp0; scal[4] = ls.qs; scal[5] = ls.qd2;
+    }
+  }
+  __syncthreads();
+  const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3], qs = scal[4], qd2 = scal[5];
+  const int stride = (k + 1) * CI_TC;
+  float* rs = rscr + b * (long)(2 * T);       // [T] residuals, then [T] rbar
+  // ---- pre-pass: residuals ---------------------------------------------------------------------------
+  for (int t = tid; t < T; t += NT) {
+    const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) acc = fmaf(beta[j], __ldg(xp + j * CI_TC), acc);
+    rs[t] = __ldg(xp + k * CI_TC) - acc;
+  }
+  // ---- initial state ---------------------------------------------------------------------------------
+  {
+    const float m0 = sconst[SC_M0 * L.N + n], p0 = sconst[SC_P0 * L.N + n], sd = sconst[SC_SD * L.N + n];
+    const float off = S > 1 ? -p0 / (float)S : 0.f, off2 = S2 > 1 ? -p0 / (float)S2 : 0.f;
+    for (int e = tid; e < D * D; e += NT) {
+      const int i = e / D, j = e % D;
+      float v = 0.f;
+      if (i < so || j < so) {
+        if (i == j) v = (i == 0) ? p0 : sd * sd;
+      } else if (i < so2 && j < so2) {
+        v = (i == j) ? p0 + off : off;
+      } else if (i >= so2 && j >= so2) {
+        v = (i == j) ? p0 + off2 : off2;
+      }
+      P[e] = v;
+      Pb[e] = 0.f;
+    }
+    for (int j = tid; j < D; j += NT) {
+      m[j] = (j == 0) ? m0 : 0.f;
+      mb[j] = 0.f;
+    }
+  }
+  __syncthreads();
+  float* tp = tape + b * (long)T * (D + 1);
+  float acc = 0.f, quad = 0.f;      // thread 0: sums of log s_t and v_t^2 / s_t
+  int nobs = 0;
+  float r_next = rs[0];
+  SeasonWalk<TWO> walk(L, so, so2, 0);
+  for (int t = 0; t < T; ++t, walk.next()) {
+    const BigSeason z = walk.get();
+    const int J = z.J, J2 = z.J2;
+    const float resid = r_next;
+    if (t + 1 < T) r_next = rs[t + 1];
+    const bool obs = (resid == resid);
+    // phase A: g = P H^T (column reads), H m
+    float gj = 0.f;
+    if (ty == 0 && col_ok) {
+      gj = P[tx * D] + (S > 1 ? P[tx * D + J] : 0.f) + (TWO ? P[tx * D + J2] : 0.f);
+      g[tx] = gj;
+    }
+    const float hm = m[0] + (S > 1 ? m[J] : 0.f) + (TWO ? m[J2] : 0.f);
+    __syncthreads();
+    const float s = g[0] + (S > 1 ? g[J] : 0.f) + (TWO ? g[J2] : 0.f) + R;
+    const float v = resid - hm;
+    const float is = rcp(s);
+    const float nis = obs ? -is : 0.f;
+    const float qq = z.change ? qd : 0.f, qq2 = z.change2 ? qd2 : 0.f;
+    // phase C: mean update, covariance sweep (measurement + time update), tape
+    if (col_ok) {
+      if (ty == 0 && obs) m[tx] = fmaf(gj, v * is, m[tx]);
+      const float gx = g[tx];
+      const float wx = drift_w(tx, z.c, S, so), w2x = TWO ? drift_w(tx, z.c2, S2, so2) : 0.f;
+#pragma unroll 4
+      for (int i = ty; i < D; i += RG) {
+        float nv = fmaf(qq * drift_w(i, z.c, S, so), wx, fmaf(g[i] * nis, gx, P[i * D + tx]));
+        if (TWO) nv = fmaf(qq2 * drift_w(i, z.c2, S2, so2), w2x, nv);
+        if (so != 2 && i == 0 && tx == 0) nv += ql;     // level variance (LocalLinearTrend: after F P F^T below)
+        P[i * D + tx] = nv;
+      }
+      if (ty == RG - 1) tp[(long)t * (D + 1) + tx] = gx;
+    }
+    if (tid == NT - 1) tp[(long)t * (D + 1) + D] = obs ? v : __int_as_float(0x7fc00000);
+    if (tid == 0 && obs) {
+      acc += logf(s);
+      quad = fmaf(v * is, v, quad);
+      ++nobs;
+    }
+    __syncthreads();
+    if (so == 2) {   // LocalLinearTrend transition: P <- F P F^T, m <- F m
+      if (ty == 0 && col_ok) P[tx] += P[D + tx];
+      __syncthreads();
+      if (ty == 0 && col_ok) P[tx * D] += P[tx * D + 1];
+      if (tid == 0) m[0] += m[1];
+      __syncthreads();
+      if (tid == 0) {
+        P[D + 1] += qs;
+        P[0] += ql;
+      }
+      __syncthreads();
+    }
+  }
+  const float ll = -0.5f * (acc + quad + (float)nobs * CI_LOG_2PI);
+
+  // ---- reverse sweep -----------------------------------------------------------------------------------
+  float Rb = 0.f, qlb = 0.f, qsb = 0.f, qdb = 0.f, qd2b = 0.f;     // thread 0
+  float cur_g = col_ok ? tp[(long)(T - 1) * (D + 1) + tx] : 0.f, cur_v = tp[(long)(T - 1) * (D + 1) + D];
+  walk = SeasonWalk<TWO>(L, so, so2, T - 1);
+  for (int t = T - 1; t >= 0; --t, walk.prev()) {
+    const BigSeason z = walk.get();
+    const int J = z.J, J2 = z.J2;
+    float nxt_g = 0.f, nxt_v = 0.f;
+    if (t > 0) {
+      nxt_g = col_ok ? tp[(long)(t - 1) * (D + 1) + tx] : 0.f;
+      nxt_v = tp[(long)(t - 1) * (D + 1) + D];
+    }
+    const float v = cur_v;
+    const bool obs = (v == v);
+    const float gx = obs ? cur_g : 0.f;
+    if (ty == 0 && col_ok) g[tx] = gx;
+    if (tid == 0) qlb += Pb[0];
+    if (so == 2) {   // adjoint of the LocalLinearTrend transition
+      if (tid == 0) qsb += Pb[D + 1];
+      __syncthreads();
+      if (ty == 0 && col_ok) Pb[D + tx] += Pb[tx];
+      __syncthreads();
+      if (ty == 0 && col_ok) Pb[tx * D + 1] += Pb[tx * D];
+      if (tid == 0) mb[1] += mb[0];
+    }
+    __syncthreads();
+    // partial column sums over this thread's rows: Pbar g and Pbar w (drift adjoints)
+    {
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (col_ok && (obs || z.change || z.change2)) {
+#pragma unroll 4
+        for (int i = ty; i < D; i += RG) {
+          const float pb = Pb[i * D + tx];
+          c0 = fmaf(pb, g[i], c0);
+          c1 = fmaf(pb, drift_w(i, z.c, S, so), c1);
+          if (TWO) c2 = fmaf(pb, drift_w(i, z.c2, S2, so2), c2);
+        }
+      }
+      part[(0 * RG + ty) * CTA_COLS + tx] = c0;
+      part[(1 * RG + ty) * CTA_COLS + tx] = c1;
+      part[(2 * RG + ty) * CTA_COLS + tx] = c2;
+    }
+    __syncthreads();
+    float col = 0.f;
+    if (ty == 0) {    // warps 0 and 1: finish the column sums and reduce the four scalars
+      float nac = 0.f, nac2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < RG; ++q) {
+        col += part[(0 * RG + q) * CTA_COLS + tx];
+        nac += part[(1 * RG + q) * CTA_COLS + tx];
+        nac2 += part[(2 * RG + q) * CTA_COLS + tx];
+      }
+      const float wx = col_ok ? drift_w(tx, z.c, S, so) : 0.f;
+      const float w2x = (TWO && col_ok) ? drift_w(tx, z.c2, S2, so2) : 0.f;
+      const float pa = col_ok ? mb[tx] * gx : 0.f;
+      const float pg = gx * col;
+      const float s0 = warp_sum(pa), s1 = warp_sum(pg), s2 = warp_sum(wx * nac), s3 = warp_sum(w2x * nac2);
+      if ((tid & 31) == 0) {
+        float* rr = red + (tid >> 5) * 4;
+        rr[0] = s0; rr[1] = s1; rr[2] = s2; rr[3] = s3;
+      }
+    }
+    __syncthreads();
+    const float a = red[0] + red[4], gPg = red[1] + red[5];
+    if (tid == 0) {
+      if (z.change) qdb += red[2] + red[6];
+      if (TWO && z.change2) qd2b += red[3] + red[7];
+    }
+    float gb = 0.f, vb = 0.f;
+    if (obs) {
+      const float s = g[0] + (S > 1 ? g[J] : 0.f) + (TWO ? g[J2] : 0.f) + R;
+      const float is = rcp(s);
+      const float vis = v * is;
+      vb = (a - v) * is;
+      const float sbar = (gPg - a * v) * is * is - 0.5f * (is - vis * vis);
+      if (tid == 0) Rb += sbar;
+      if (ty == 0 && col_ok) {
+        const bool inH = tx == 0 || (S > 1 && tx == J) || (TWO && tx == J2);
+        gb = fmaf(mb[tx], vis, fmaf(-2.f * is, col, inH ? sbar : 0.f));
+        const float h = 0.5f * gb;     // Pbar += sym(gb H^T): level row / column first
+        Pb[tx * D] += h;
+        Pb[tx] += h;
+      }
+    }
+    if (tid == 0) rs[T + t] = obs ? vb : 0.f;
+    __syncthreads();
+    if (obs) {
+      if (S > 1 && ty == 0 && col_ok) {
+        const float h = 0.5f * gb;
+        Pb[tx * D + J] += h;
+        Pb[J * D + tx] += h;
+      }
+      if (tid == 0) {
+        mb[0] -= vb;
+        if (S > 1) mb[J] -= vb;
+        if (TWO) mb[J2] -= vb;
+      }
+    }
+    if (TWO) {
+      __syncthreads();
+      if (obs && ty == 0 && col_ok) {
+        const float h = 0.5f * gb;
+        Pb[tx * D + J2] += h;
+        Pb[J2 * D + tx] += h;
+      }
+    }
+    cur_g = nxt_g;
+    cur_v = nxt_v;
+    __syncthreads();
+  }
+  // ---- post-pass: beta_bar_j = -sum_t rbar_t X_tj  (threads = covariates x time slices) -----------------
+  if (k > 0) {
+    const int slices = NT / kk > 0 ? NT / kk : 1;
+    float* pb = part;   // [slices][k] partial sums (3 RG 64 floats >= NT available)
+    const int j = tid % kk, sl = tid / kk;
+    if (sl < slices) {
+      float accb = 0.f;
+      for (int t = sl; t < T; t += slices) {
+        const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
+        accb = fmaf(-rs[T + t], __ldg(xp + j * CI_TC), accb);
+      }
+      pb[sl * kk + j] = accb;
+    }
+    __syncthreads();
+    if (tid < k) {
+      float accb = 0.f;
+      for (int q = 0; q < slices; ++q) accb += pb[q * kk + tid];
+      beta[tid] = accb;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (!big_gen(L)) params_backward_lane(u + b, B, k, S, sconst + n, L.N, beta, 1, Rb, qlb, qdb, grad + b);
+    else params_backward_gen(u + b, B, k, S, L.flags, sconst + n, L.N, beta, 1, Rb, qlb, qsb, qdb, grad + b, L.S2, qd2b);
+    logp[b] = ll + lp0;
+  }
+}
+
+template <int RG>
+static size_t cta_smem_bytes(const ci_layout* L) {
+  const int D = big_D(*L);
+  return (size_t)(2 * D * D + 3 * D + 3 * RG * CTA_COLS + 16 + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
+}
+
+// CTA-per-lane pays when the lanes cannot fill the machine with warps
+bool big_use_cta(const ci_layout* L) {
+  const long B = (long)L->N * L->G;
+  return big_D(*L) <= CTA_COLS && big_D(*L) >= 8 && B <= 2 * 148 && L->k <= 256 &&
+         cta_smem_bytes<8>(L) <= 227 * 1024;
+}
+
 size_t big_smem_bytes(const ci_layout* L) {
   const int D = big_D(*L);
   return (size_t)BIG_WARPS * (2 * D * D + 4 * D + (L->k > 0 ? L->k : 1) + 8) * sizeof(float);
@@ -827,7 +1144,7 @@ bool big_supported(const ci_layout* L) {
 
 size_t big_tape_floats(const ci_layout* L) {
   const size_t D = big_D(*L);
-  return (size_t)L->N * L->G * L->T * (D + 1);
+  return (size_t)L->N * L->G * L->T * (D + 1 + 2);   // + residuals / rbar scratch of the CTA-per-lane kernel
 }
 
 size_t big_fstate_floats(const ci_layout* L) {
@@ -847,6 +1164,23 @@ static int big_attr(K kern, size_t smem) {
 int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                     float* tape, cudaStream_t st) {
   if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  if (big_use_cta(L)) {
+#ifndef CI_CTA_RG
+#define CI_CTA_RG 8
+#endif
+    constexpr int RG = CI_CTA_RG;
+    const size_t smem = cta_smem_bytes<RG>(L);
+    const long B = (long)L->N * L->G;
+    float* rscr = tape + (size_t)B * L->T * (big_D(*L) + 1);
+    if (L->S2 > 1) {
+      if (int e = big_attr(k_eval_cta<RG, true>, smem)) return e;
+      k_eval_cta<RG, true><<<(unsigned)B, CTA_COLS * RG, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, rscr);
+    } else {
+      if (int e = big_attr(k_eval_cta<RG, false>, smem)) return e;
+      k_eval_cta<RG, false><<<(unsigned)B, CTA_COLS * RG, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, rscr);
+    }
+    return CI_OK;
+  }
   const size_t smem = big_smem_bytes(L);
   const long B = (long)L->N * L->G;
   const unsigned grid = (unsigned)((B + BIG_WARPS - 1) / BIG_WARPS);
