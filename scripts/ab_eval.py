@@ -10,7 +10,7 @@ nt._LIB_PATH = sys.argv[1]
 import numpy as np, torch
 from tfcausalimpact_b200.engine import DeviceBatch
 it = int(sys.argv[2])
-N, G, T, Tf, k, S = 10000, 8, 365, 30, 50, 7
+N, G, T, Tf, k, S = int(os.environ.get('AB_N', 10000)), 8, 365, 30, int(os.environ.get('AB_K', 50)), 7
 rng = np.random.default_rng(0)
 y = rng.normal(size=(N, T)).astype(np.float32)
 X = rng.normal(size=(N, T + Tf, k)).astype(np.float32)

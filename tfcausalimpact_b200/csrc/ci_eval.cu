@@ -122,8 +122,13 @@ __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ gra
 // registers and one of them must host 5 of the 17 warps (5 x 32 x 104 > 16384).  Measured with
 // __maxnreg__: 104 / 112 / 120 registers -> 1.26 / 1.15 / 1.11 ms (second wave) against 0.87 ms at 96
 // (unconstrained, ptxas would take 192).
-template <int S, bool STAGED, bool EFF>
-__global__ void __launch_bounds__(EVAL_THREADS, (S <= 7 ? 20 : 8))
+// SMALL = true is the few-lanes instantiation (B <= CI_SMALL_LANES: at most about one warp per scheduler):
+// nothing hides latency there, so the register cap is lifted and ptxas schedules for ILP (166 registers, no
+// spills): 0.336 -> 0.301 ms per evaluation at 1000 series x 8 chains.  (Prefetching the next tape entry into
+// registers instead of L2 was measured too: 0.310 ms.)
+#define CI_SMALL_LANES (148 * 4 * 32)
+template <int S, bool STAGED, bool EFF, bool SMALL>
+__global__ void __launch_bounds__(EVAL_THREADS, (SMALL ? 10 : (S <= 7 ? 20 : 8)))
 k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
        float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, LeapArgs lf) {
   extern __shared__ __align__(16) float smem[];
@@ -264,13 +269,13 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
   k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(*L, D->d_sconst, d_u, beta, scal);
 }
 
-template <int S, bool STAGED, bool EFF>
+template <int S, bool STAGED, bool EFF, bool SMALL>
 static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                          const EvalWs& ws, cudaStream_t st, const LeapArgs& lf) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
   if (STAGED) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
-  auto kern = k_eval<S, STAGED, EFF>;
+  auto kern = k_eval<S, STAGED, EFF, SMALL>;
   if (smem > 48 * 1024) {
     if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -299,13 +304,18 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
     return CI_OK;
   }
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
+  const bool small = eff && (long)L->N * L->G <= CI_SMALL_LANES;
+#define CI_EFF_S(S_) (S_ >= 2 && S_ <= CI_MAX_EFF_S)
   if (use_staging(L)) {
-    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    if (small) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, CI_EFF_S(S_), CI_EFF_S(S_)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, CI_EFF_S(S_), false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
   } else {
-    if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, (S_ >= 2 && S_ <= CI_MAX_EFF_S)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    if (small) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, CI_EFF_S(S_), CI_EFF_S(S_)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, CI_EFF_S(S_), false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
   }
+#undef CI_EFF_S
   if (rc) return rc;
   CI_CHECK_LAUNCH();
   return CI_OK;
