@@ -65,3 +65,30 @@ def test_reference_known_answer_p_value():
     summ = db.reduce_summary(torch.as_tensor(y_post).cuda(), torch.zeros(1, 3).cuda() + 1,
                              torch.as_tensor(sims).cuda(), 0.05).cpu().numpy()
     assert abs(summ[0, 20] - O.p_value(sims[0], y_post.sum())) < 1e-7
+
+
+@pytest.mark.parametrize('nsamp', [1000, 1024, 1025, 2048, 33])
+def test_percentiles_with_ties_and_negative_values(nsamp):
+    """The radix-select path (<= 2048 draws) on columns full of ties, negative values and signed zeros."""
+    from tfcausalimpact_b200.engine import DeviceBatch
+    rng = np.random.default_rng(nsamp)
+    N, T, Tf = 2, 11, 6
+    y_pre = rng.normal(size=(N, T)).astype(np.float32)
+    y_post = rng.normal(size=(N, Tf)).astype(np.float32)
+    pre_sims = rng.integers(-3, 4, size=(N, nsamp, T)).astype(np.float32)          # heavy ties, both signs
+    pre_sims[:, ::7, :] *= -0.0
+    pre_sims[:, :, 0] = 5.0                                                          # constant column
+    pre_sims[:, :, 1] = -np.abs(rng.normal(size=(N, nsamp))).astype(np.float32)      # all negative
+    post_sims = (rng.normal(size=(N, nsamp, Tf)) * 1e-3).astype(np.float32)
+    pre_mean = pre_sims.mean(axis=1).astype(np.float32)
+    post_mean = post_sims.mean(axis=1).astype(np.float32)
+    db = DeviceBatch(y_pre, None, Tf=Tf)
+    dev = [torch.as_tensor(a).cuda() for a in (y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean)]
+    inf = db.reduce_inferences(*dev, 0.05).cpu().numpy()
+    for n in range(N):
+        lo, hi = O.percentiles(pre_sims[n], 0.05)
+        np.testing.assert_allclose(inf[n, 1, :T], lo, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(inf[n, 2, :T], hi, rtol=1e-6, atol=1e-7)
+        lo, hi = O.percentiles(post_sims[n], 0.05)
+        np.testing.assert_allclose(inf[n, 4, :Tf], lo, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(inf[n, 5, :Tf], hi, rtol=1e-6, atol=1e-9)
