@@ -169,6 +169,33 @@ def test_default_model_spec(rand_data):
     assert 'Customized Linear Regression Models must have total' in str(e.value)
 
 
+def test_custom_model_lowering_without_gpu():
+    """Sum -> layout flags / parameter names for the wider model set (reference main.py:180-252, notebook
+    cell 116): LocalLinearTrend, dense LinearRegression, up to two Seasonal components; everything else
+    is rejected."""
+    from tfcausalimpact_b200 import _native as nt
+    obs = pd.Series(np.arange(40, dtype=np.float32))
+    X = np.zeros((50, 3), np.float32)
+    m = cimodel.Sum([cimodel.LocalLinearTrend(observed_time_series=obs), cimodel.LinearRegression(design_matrix=X),
+                     cimodel.Seasonal(num_seasons=4, name='Month'), cimodel.Seasonal(num_seasons=52, name='Year')],
+                    observed_time_series=obs)
+    assert m.flags == nt.FLAG_LLT | nt.FLAG_DENSE_REG | nt.FLAG_OBS_LOGNORMAL
+    assert m.param_names() == ['observation_noise_scale', 'LocalLinearTrend/_level_scale',
+                               'LocalLinearTrend/_slope_scale', 'LinearRegression/_weights',
+                               'Month/_drift_scale', 'Year/_drift_scale']
+    assert nt.num_params(3, 4, m.flags, 52) == 1 + 2 + 3 + 2
+    assert [(n, b - a) for n, a, b, _ in m.param_slices()][3] == ('LinearRegression/_weights', 3)
+    with pytest.raises(ValueError):      # three Seasonal components
+        cimodel.Sum([cimodel.LocalLevel(), cimodel.Seasonal(2, name='a'), cimodel.Seasonal(3, name='b'),
+                     cimodel.Seasonal(4, name='c')], observed_time_series=obs)
+    with pytest.raises(ValueError):      # same name twice
+        cimodel.Sum([cimodel.LocalLevel(), cimodel.Seasonal(4), cimodel.Seasonal(7)], observed_time_series=obs)
+    with pytest.raises(ValueError):      # seasonal before the trend
+        cimodel.Sum([cimodel.Seasonal(4), cimodel.LocalLevel()], observed_time_series=obs)
+    with pytest.raises(ValueError):      # two trends
+        cimodel.Sum([cimodel.LocalLevel(), cimodel.LocalLinearTrend()], observed_time_series=obs)
+
+
 def test_no_cpu_fallback(monkeypatch):
     """The product path must fail loudly without CUDA."""
     import torch
