@@ -158,3 +158,51 @@ def test_two_seasonal_components_logp_grad_matches_oracle(flags, S, r, S2, r2, k
     ud = torch.as_tensor(u).cuda()
     th = db.constrain(ud)
     np.testing.assert_allclose(db.unconstrain(th).cpu().numpy(), u, rtol=2e-4, atol=2e-4)
+
+
+# edge shapes: series shorter than a staging chunk / the tape prefetch distance / one season cycle, single
+# lane, single covariate, a masked run at the very start after the first observation
+EDGE_CASES = [
+    # S, r, k, T, N, G, masked steps
+    (1, 1, 0, 2, 1, 1, ()),
+    (1, 1, 1, 3, 2, 1, (1,)),
+    (7, 1, 50, 5, 3, 8, (1, 2)),          # staged effects path, T < 8 (no tape prefetch), T < S
+    (7, 1, 4, 9, 1, 4, (3,)),
+    (2, 1, 2, 4, 2, 2, ()),
+    (3, 2, 1, 7, 1, 3, (1, 2, 3)),
+    (52, 1, 0, 6, 1, 1, ()),              # CTA-per-lane kernel, T << S
+    (9, 1, 3, 5, 40, 8, (2,)),            # warp-per-lane kernel
+]
+
+
+@pytest.mark.parametrize('S,r,k,T,N,G,masked', EDGE_CASES)
+def test_edge_shapes_match_oracle(S, r, k, T, N, G, masked):
+    from tfcausalimpact_b200.engine import DeviceBatch
+    Tf = 3
+    L = O.Layout(T, Tf, k, S, r)
+    y, _, X = synth_problem(N, T, Tf, k, S, r, seed=900 + S + T)
+    for t in masked:
+        y[:, t] = np.nan
+    prob = O.Problem.build(y, X, L, dtype=torch.float64)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S, season_duration=r)
+    rng = np.random.default_rng(4)
+    B = N * G
+    u = (rng.normal(size=(L.P, B)) * 0.5).astype(np.float32)
+    u[0] -= 1.0
+    u[1] -= 2.0
+    lp, g = db.logp_grad(torch.as_tensor(u).cuda())
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    series = torch.arange(B) // G
+    lpo, go = O.target_log_prob_and_grad(prob, torch.tensor(u.T.astype(np.float64)), series)
+    lpo, go = lpo.numpy(), go.numpy().T
+    np.testing.assert_allclose(lp, lpo, rtol=1e-4, atol=1e-4)
+    gmax = np.abs(go).max(axis=0, keepdims=True)
+    assert np.all(np.abs(g - go) <= 1e-4 * np.abs(go) + 2e-5 * gmax)
+    # the predictive path on the same tiny shapes
+    ud = torch.as_tensor(u).cuda()
+    pm, pv, fs = db.filter_predict(ud)
+    mean_o, var_o, _, _, _, _ = O.one_step_predictive(prob, torch.as_tensor(u.T.astype(np.float64)), series)
+    np.testing.assert_allclose(pm.cpu().numpy().T, mean_o.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(pv.cpu().numpy().T, var_o.numpy(), rtol=1e-4)
+    sims, mean = db.forecast_sample(ud, fs, 64, seed=1)
+    assert torch.isfinite(sims).all() and torch.isfinite(mean).all()
