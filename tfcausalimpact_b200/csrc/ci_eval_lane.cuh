@@ -64,7 +64,7 @@ struct XDirect {
 // tape : [T][S+1] with element stride ldt
 // u, grad : [P] with element stride ld
 template <int S, class XS>
-CI_HD void eval_lane(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs, int T,
+CI_HD void eval_lane(const float* u, long ld, const float* __restrict__ sc, long scld, XS& xs, int T,
                      int k, int r_dur, float* __restrict__ sb, int sbld, float* __restrict__ sr,
                      float* __restrict__ tape, long ldt, float* __restrict__ logp_out, float* __restrict__ grad) {
   constexpr int TW = S + 1;
@@ -408,7 +408,7 @@ struct EffLane {
 // scratch column stride SBLD is a compile-time constant so the regression loops address shared
 // memory with immediates.
 template <int S, int TQ, int SBLD, class XS>
-CI_HD void eval_lane_eff(const float* __restrict__ u, long ld, const float* __restrict__ sc, long scld, XS& xs,
+CI_HD void eval_lane_eff(const float* u, long ld, const float* __restrict__ sc, long scld, XS& xs,
                          int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
                          int tstep, float* __restrict__ logp_out, float* __restrict__ grad, int pfrow = -1) {
   const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, SBLD, -1.0f);   // sb <- -beta

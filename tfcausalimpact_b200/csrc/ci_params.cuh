@@ -42,7 +42,7 @@ struct LaneScalars {
 };
 
 // u, beta: element stride `ld`.  sc: pointer to this series' constants with field stride `scld`.
-CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int k, int S,
+CI_HD LaneScalars params_forward_lane(const float* u, long ld, int k, int S,
                                       const float* __restrict__ sc, long scld, float* __restrict__ beta,
                                       long ldb, float beta_sign = 1.0f) {
   const float sd = sc[SC_SD * scld];
@@ -113,7 +113,7 @@ CI_HD LaneScalars params_forward_lane(const float* __restrict__ u, long ld, int 
 
 // grad[i] = d/du_i [ log prior + log-det + log-lik ], given the filter adjoints
 // (Rb, qlb, qdb) and beta_bar = dloglik/dbeta (stride ldb).
-CI_HD void params_backward_lane(const float* __restrict__ u, long ld, int k, int S,
+CI_HD void params_backward_lane(const float* u, long ld, int k, int S,
                                 const float* __restrict__ sc, long scld,
                                 const float* __restrict__ beta_bar, long ldb, float Rb, float qlb, float qdb,
                                 float* __restrict__ grad) {
