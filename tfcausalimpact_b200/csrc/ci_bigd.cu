@@ -560,7 +560,7 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
   float x[CI_BIG_MAXD];
   for (int a = 0; a < D; ++a) x[a] = fs[a];
   for (int q = 0; q < (D + 3) / 4; ++q) {
-    const f32x4 zz = philox_normal4((uint32_t)si, (uint32_t)q, 0u, TAG_FORECAST_X0, seed);
+    const f32x4 zz = philox_normal4_fast((uint32_t)si, (uint32_t)q, 0u, TAG_FORECAST_X0, seed);
     const float z4[4] = {zz.x, zz.y, zz.z, zz.w};
     for (int e = 0; e < 4; ++e) {
       const int col = 4 * q + e;
@@ -574,7 +574,7 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
     for (int q = 0; q < tn; ++q) {
       const int t = t0 + q;
       const int c = S > 1 ? season_of(L.T + t, S, r) : 0;
-      const f32x4 e = philox_normal4((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
+      const f32x4 e = philox_normal4_fast((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
       const int c2 = S2 > 1 ? season_of(L.T + t, S2, L.r2) : 0;
       const float yv = x[0] + (S > 1 ? x[so + c] : 0.f) + (S2 > 1 ? x[so2 + c2] : 0.f) + off[(long)t * B + b] + sobs * e.x;
       tile[threadIdx.x][q] = fmaf(yv, sg, mu);
@@ -589,7 +589,7 @@ k_forecast_sample_big(ci_layout L, int nsamp, uint64_t seed, const float* __rest
         x[so + c] -= (float)S * xi;    // net -(S-1) xi on the season just observed
       }
       if (season_change(L.T + t, S2, L.r2)) {   // second seasonal component: its own drift draw
-        const float xi = sdr2 * philox_normal4((uint32_t)si, (uint32_t)t, 1u, TAG_FORECAST, seed).x;
+        const float xi = sdr2 * philox_normal4_fast((uint32_t)si, (uint32_t)t, 1u, TAG_FORECAST, seed).x;
         for (int a = so2; a < D; ++a) x[a] += xi;
         x[so2 + c2] -= (float)S2 * xi;
       }

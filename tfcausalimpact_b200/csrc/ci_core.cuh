@@ -190,6 +190,21 @@ CI_HD f32x4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, 
   return f32x4{r0 * c0f, r0 * s0, r1 * c1f, r1 * s1};
 }
 
+// Same Philox stream, Box-Muller on the special-function unit (MUFU lg2 / sin / cos / sqrt, angle in
+// [-pi, pi)): for the posterior-predictive SAMPLERS only, whose contract is distributional (absolute error
+// of a draw ~1e-6); the fit drivers keep philox_normal4, which the oracle reproduces.
+CI_HD f32x4 philox_normal4_fast(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, uint64_t seed) {
+#if defined(__CUDA_ARCH__)
+  const f32x4 u = philox_uniform4(c0, c1, c2, tag, seed);
+  const float r0 = __fsqrt_rn(-2.0f * __logf(u.x)), r1 = __fsqrt_rn(-2.0f * __logf(u.z));
+  const float two_pi = 6.283185307179586f;
+  const float a0 = two_pi * (u.y - 0.5f), a1 = two_pi * (u.w - 0.5f);
+  return f32x4{r0 * __cosf(a0), r0 * __sinf(a0), r1 * __cosf(a1), r1 * __sinf(a1)};
+#else
+  return philox_normal4(c0, c1, c2, tag, seed);
+#endif
+}
+
 // Stream tags (counter word 3) -- keep in sync with oracle/sts_oracle.py TAG_*.
 enum : uint32_t {
   TAG_VI_INIT = 1,

@@ -136,7 +136,7 @@ k_onestep_sample(int N, int G, int T, int nsamp, uint64_t seed, const float* __r
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
       // counter = (sample, time quad): the same stream as one Philox call per 4 consecutive steps
-      const f32x4 z = philox_normal4((uint32_t)si, (uint32_t)((t0 >> 2) + q4), 0u, TAG_ONESTEP, seed);
+      const f32x4 z = philox_normal4_fast((uint32_t)si, (uint32_t)((t0 >> 2) + q4), 0u, TAG_ONESTEP, seed);
       const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -222,7 +222,7 @@ k_forecast_sample(int N, int G, int T, int Tf, int r, int nsamp, uint64_t seed,
     float z[S];
 #pragma unroll
     for (int q = 0; q < (S + 3) / 4; ++q) {
-      const f32x4 zz = philox_normal4((uint32_t)si, (uint32_t)q, 0u, TAG_FORECAST_X0, seed);
+      const f32x4 zz = philox_normal4_fast((uint32_t)si, (uint32_t)q, 0u, TAG_FORECAST_X0, seed);
       if (4 * q + 0 < S) z[4 * q + 0] = zz.x;
       if (4 * q + 1 < S) z[4 * q + 1] = zz.y;
       if (4 * q + 2 < S) z[4 * q + 2] = zz.z;
@@ -242,7 +242,7 @@ k_forecast_sample(int N, int G, int T, int Tf, int r, int nsamp, uint64_t seed,
     const int tn = min(32, Tf - t0);
     for (int q = 0; q < tn; ++q) {
       const int t = t0 + q;
-      const f32x4 e = philox_normal4((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
+      const f32x4 e = philox_normal4_fast((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
       const float yv = x[0] + (S > 1 ? x[1] : 0.f) + off[(long)t * B + b] + so * e.x;
       tile[threadIdx.x][q] = fmaf(yv, sg, mu);
       x[0] = fmaf(sl, e.y, x[0]);
