@@ -64,6 +64,11 @@ typedef struct ci_data {
   const float* d_y;      /* [N][T]        observed series, NaN = missing step            */
   const float* d_X;      /* [Tpad/4][N][k+1][4] chunk-major covariates + y (ci_pack_design) */
   const float* d_sconst; /* [8][N]        per-series constants (see ci_series_stats)     */
+  const float* d_XT;     /* optional (may be NULL): the same design block covariate-major inside a chunk,
+                            [Tpad/4][k+1][N][4] (ci_repack_design_cov).  Used by ci_kalman_logp_grad / the fit
+                            drivers when a series has fewer than 4 lanes (e.g. 1 chain, the reference's
+                            default): every lane then stages its own series' chunk with cp.async and the 32
+                            lanes of a warp read one contiguous run per covariate.  */
 } ci_data;
 
 int ci_version(void);
@@ -90,6 +95,12 @@ int ci_series_stats(const ci_layout* L, const float* d_y, float prior_level_sd, 
  * Replaces: causalimpact/model.py:303-308 (concat(pre, post).astype(float32).fillna(0)). */
 int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d_y, const float* d_sconst,
                    float* d_XY_packed, void* stream);
+
+/* 1 when ci_kalman_logp_grad / the fit drivers would use ci_data.d_XT for this layout (fewer than 4 lanes per
+ * series and the per-lane staging slices fit in shared memory), else 0: callers build the copy only then. */
+int ci_eval_uses_xt(const ci_layout* L);
+/* Covariate-major copy of the packed block for ci_data.d_XT: XT[tc][j][n][q] = XY[tc][n][j][q]. */
+int ci_repack_design_cov(const ci_layout* L, const float* d_XY_packed, float* d_XT_packed, void* stream);
 
 /* ---- K1-K3: joint log-prob + gradient in unconstrained space ------------------------------
  * Replaces: `model.joint_log_prob(observed_time_series)` + TF autodiff, causalimpact/model.py:375-377

@@ -27,6 +27,12 @@ CASES = [
     (9, 2, 0, 75, 0.1, 2, 3),
     (10, 3, 40, 90, 0.05, 2, 2),
     (52, 1, 3, 130, 0.0, 2, 2),   # configs[4] latent size (few lanes -> CTA-per-lane kernel)
+    # fewer than 4 lanes per series with >= 8 series: covariate-major design block (ci_data.d_XT)
+    (7, 1, 6, 50, 0.05, 9, 1),
+    (5, 1, 50, 37, 0.0, 12, 2),
+    (7, 1, 3, 61, 0.1, 33, 3),
+    (1, 1, 4, 30, 0.0, 40, 1),
+    (6, 3, 5, 45, 0.1, 10, 2),     # residual-basis path (season_duration 3)
     # the same large-latent layouts with enough lanes (B > 296) to stay on the warp-per-lane kernel
     (9, 2, 2, 40, 0.1, 40, 8),
     (52, 1, 0, 60, 0.0, 50, 6),

@@ -23,7 +23,8 @@ class CiLayout(ctypes.Structure):
 
 
 class CiData(ctypes.Structure):
-    _fields_ = [('d_y', ctypes.c_void_p), ('d_X', ctypes.c_void_p), ('d_sconst', ctypes.c_void_p)]
+    _fields_ = [('d_y', ctypes.c_void_p), ('d_X', ctypes.c_void_p), ('d_sconst', ctypes.c_void_p),
+                ('d_XT', ctypes.c_void_p)]
 
 
 def lib():

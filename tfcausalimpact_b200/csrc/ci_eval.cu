@@ -66,6 +66,37 @@ struct XStaged {
     if ((threadIdx.x & 31) == 0 && next_tc >= 0) issue(next_tc);
   }
   __device__ __forceinline__ const float* chunk(int) const { return lane_x; }
+  __device__ __forceinline__ constexpr int rs() const { return CI_TC; }
+  __device__ __forceinline__ f4 load(const float* p) const {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    return f4{v.x, v.y, v.z, v.w};
+  }
+};
+
+// Few lanes per series (G < 4: one chain / one VI sample per series, the reference's defaults): every lane copies
+// ITS OWN series' chunk -- k + 1 rows of 16 bytes -- from the covariate-major block XT [chunk][k+1][N][4] into a
+// private shared-memory slice with cp.async (the 32 lanes of a warp read one contiguous run per row), one chunk
+// ahead of the filter steps.  No barrier of any kind: the slice is private, completion is per thread.
+struct XAsync {
+  const float* lane_x;   // this lane's slice [k+1][4] (shared memory)
+  uint32_t sx_addr;      // ... shared-space address
+  const float* gsrc;     // XT[0][0][n] (global)
+  long cstride;          // floats between consecutive chunks = N * (k + 1) * CI_TC
+  int rows;              // k + 1
+  int grow;              // global floats between rows = N * CI_TC
+  __device__ __forceinline__ void issue(int tc) const {
+    const float* g = gsrc + (long)tc * cstride;
+    for (int j = 0; j < rows; ++j)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (uint32_t)j * 16u), "l"(g + (long)j * grow)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void acquire() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  __device__ __forceinline__ void release(int next_tc) const {
+    if (next_tc >= 0) issue(next_tc);
+  }
+  __device__ __forceinline__ const float* chunk(int) const { return lane_x; }
+  __device__ __forceinline__ constexpr int rs() const { return CI_TC; }
   __device__ __forceinline__ f4 load(const float* p) const {
     const float4 v = *reinterpret_cast<const float4*>(p);
     return f4{v.x, v.y, v.z, v.w};
@@ -127,10 +158,12 @@ __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ gra
 // spills): 0.336 -> 0.301 ms per evaluation at 1000 series x 8 chains.  (Prefetching the next tape entry into
 // registers instead of L2 was measured too: 0.310 ms.)
 #define CI_SMALL_LANES (148 * 4 * 32)
-template <int S, bool STAGED, bool EFF, bool SMALL>
+// XM: 0 = lanes read their chunks directly, 1 = TMA-staged per warp from the series-major block (>= 4 lanes per
+// series), 2 = cp.async-staged per lane from the covariate-major block (< 4 lanes per series).
+template <int S, int XM, bool EFF, bool SMALL>
 __global__ void __launch_bounds__(EVAL_THREADS, (SMALL ? 10 : (S <= 7 ? 20 : 8)))
-k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
-       float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, LeapArgs lf) {
+k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ XT, const float* __restrict__ sconst,
+       const float* u, float* __restrict__ logp, float* __restrict__ grad, float* __restrict__ tape, LeapArgs lf) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NW = EVAL_THREADS / 32;
   const long B = (long)L.N * L.G;
@@ -146,7 +179,7 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
   float* tape_eff = tape + (b >> 5) * ((ES + 1) * 32) + (b & 31);
   const int tstep_eff = (int)(nwarp * ((ES + 1) * 32));
   const int pfrow = (int)(threadIdx.x & 31) < ES + 1 ? (int)(threadIdx.x & 31) : -1;   // tape row this lane prefetches
-  if (STAGED) {
+  if (XM == 1) {
     const int w = threadIdx.x >> 5;
     const long bw0 = b - (threadIdx.x & 31);              // first lane of this warp
     if (bw0 >= B) return;                                 // whole warp is padding: nothing to wait for
@@ -181,6 +214,17 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ scon
     } else {
       idle_lane(xs, L.T);
     }
+  } else if (XM == 2) {
+    if (!valid) return;
+    float* sx = smem + (4 + L.k) * EVAL_THREADS + (long)threadIdx.x * stride;     // private [k+1][4] slice
+    XAsync xs{sx, smem_u32(sx), XT + (long)n * CI_TC, cstride, L.k + 1, L.N * CI_TC};
+    xs.issue(0);
+    if (EFF)
+      eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
+                                          logp + b, grad + b, pfrow);
+    else
+      eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
+    leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);
   } else {
     if (!valid) return;
     XDirect xs{XY + (long)n * stride, cstride};
@@ -269,26 +313,38 @@ void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_
   k_params_forward<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(*L, D->d_sconst, d_u, beta, scal);
 }
 
-template <int S, bool STAGED, bool EFF, bool SMALL>
+template <int S, int XM, bool EFF, bool SMALL>
 static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                          const EvalWs& ws, cudaStream_t st, const LeapArgs& lf) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
-  if (STAGED) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
-  auto kern = k_eval<S, STAGED, EFF, SMALL>;
+  if (XM == 1) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
+  if (XM == 2) smem += (size_t)EVAL_THREADS * (L->k + 1) * CI_TC * sizeof(float);
+  auto kern = k_eval<S, XM, EFF, SMALL>;
   if (smem > 48 * 1024) {
     if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory column budget", L->k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(*L, D->d_X, D->d_sconst, d_u,
-                                                                                      d_logp, d_grad, ws.tape, lf);
+  kern<<<(unsigned)((B + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, smem, st>>>(
+      *L, D->d_X, XM == 2 ? D->d_XT : nullptr, D->d_sconst, d_u, d_logp, d_grad, ws.tape, lf);
   return CI_OK;
 }
 
 // Staging pays when several lanes share a series (the staged run is then smaller than the beta
 // column it sits beside); single-lane-per-series calls read X directly.
 static bool use_staging(const ci_layout* L) { return L->G >= 4 && L->k >= 4; }
+// Fewer than 4 lanes per series: per-lane cp.async staging from the covariate-major copy, when the caller supplied
+// one and the private slices of all resident CTAs fit in shared memory (32 x (k + 1) x 16 bytes per warp).
+static bool async_staging_fits(const ci_layout* L) {
+  if (!ci_reg_path(L) || L->G >= 4 || L->k < 1) return false;
+  const long nwarps = ((long)L->N * L->G + 31) / 32;
+  const long ctas_per_sm = (nwarps + 147) / 148;
+  const size_t per_cta = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float) +
+                         (size_t)EVAL_THREADS * (L->k + 1) * CI_TC * sizeof(float) + 1024;
+  return per_cta * (size_t)ctas_per_sm <= (size_t)227 * 1024;
+}
+static bool use_async_staging(const ci_layout* L, const ci_data* D) { return D->d_XT && async_staging_fits(L); }
 
 int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                 const EvalWs& ws, cudaStream_t st, const LeapArgs* leap) {
@@ -306,15 +362,16 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   const bool small = eff && (long)L->N * L->G <= CI_SMALL_LANES;
 #define CI_EFF_S(S_) (S_ >= 2 && S_ <= CI_MAX_EFF_S)
-  if (use_staging(L)) {
-    if (small) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, CI_EFF_S(S_), CI_EFF_S(S_)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, CI_EFF_S(S_), false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, true, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-  } else {
-    if (small) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, CI_EFF_S(S_), CI_EFF_S(S_)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, CI_EFF_S(S_), false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
-    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, false, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }
+#define CI_EVAL_XM(XM_)                                                                                              \
+  {                                                                                                                  \
+    if (small) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, XM_, CI_EFF_S(S_), CI_EFF_S(S_)>(L, D, d_u, d_logp, d_grad, ws, st, lf))); } \
+    else if (eff) { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, XM_, CI_EFF_S(S_), false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }     \
+    else { CI_DISPATCH_S(L->S, (rc = launch_eval_t<S_, XM_, false, false>(L, D, d_u, d_logp, d_grad, ws, st, lf))); }                      \
   }
+  if (use_staging(L)) CI_EVAL_XM(1)
+  else if (use_async_staging(L, D)) CI_EVAL_XM(2)
+  else CI_EVAL_XM(0)
+#undef CI_EVAL_XM
 #undef CI_EFF_S
   if (rc) return rc;
   CI_CHECK_LAUNCH();
@@ -395,6 +452,21 @@ __global__ void k_pack_design(ci_layout L, const float* __restrict__ Xrm, const 
   XY[i] = v;
 }
 
+// Same content, covariate-major inside a chunk: XT[tc][j][n][q] = XY[tc][n][j][q]  (consecutive SERIES
+// adjacent per row).
+__global__ void k_repack_design_cov(ci_layout L, const float* __restrict__ XY, float* __restrict__ XT) {
+  const long total = (long)L.N * (L.k + 1) * L.Tpad;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // index into XT
+  if (i >= total) return;
+  const int q = (int)(i % CI_TC);
+  long rest = i / CI_TC;
+  const long n = rest % L.N;
+  rest /= L.N;
+  const int j = (int)(rest % (L.k + 1));
+  const long tc = rest / (L.k + 1);
+  XT[i] = XY[((tc * L.N + n) * (L.k + 1) + j) * CI_TC + q];
+}
+
 __global__ void k_constrain(ci_layout L, const float* __restrict__ sconst,
                             const float* __restrict__ u, float* __restrict__ theta) {
   const int N = L.N, G = L.G, k = L.k, S = L.S, flags = L.flags;
@@ -434,6 +506,17 @@ int ci_pack_design(const ci_layout* L, const float* d_X_rowmajor, const float* d
   const long total = (long)L->N * (L->k + 1) * L->Tpad;
   k_pack_design<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*L, d_X_rowmajor, d_y, d_sconst,
                                                                                    d_XY_packed);
+  CI_CHECK_LAUNCH();
+  return CI_OK;
+}
+
+int ci_eval_uses_xt(const ci_layout* L) { return (L && !check_layout(L) && async_staging_fits(L)) ? 1 : 0; }
+
+int ci_repack_design_cov(const ci_layout* L, const float* d_XY_packed, float* d_XT_packed, void* stream) {
+  if (int e = check_layout(L)) return e;
+  CI_CHECK_ARG(d_XY_packed && d_XT_packed, "NULL pointer");
+  const long total = (long)L->N * (L->k + 1) * L->Tpad;
+  k_repack_design_cov<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*L, d_XY_packed, d_XT_packed);
   CI_CHECK_LAUNCH();
   return CI_OK;
 }

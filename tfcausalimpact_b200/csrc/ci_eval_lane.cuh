@@ -42,12 +42,14 @@ CI_HD void prefetch_l2(const float* p) {
 #endif
 }
 
+
 // Direct policy: the lane reads its series' chunks straight from (global) memory.
 struct XDirect {
   const float* base;  // XY[0][n]
   long cstride;       // floats between consecutive chunks of a series = N * (k + 1) * CI_TC
   CI_HD void acquire() {}
   CI_HD void release(int /*next_tc*/) {}
+  CI_HD constexpr int rs() const { return CI_TC; }     // floats between consecutive rows of a chunk
   CI_HD const float* chunk(int tc) const { return base + (long)tc * cstride; }
   CI_HD f4 load(const float* p) const {
 #if defined(__CUDA_ARCH__)
@@ -84,12 +86,12 @@ CI_HD void eval_lane(const float* u, long ld, const float* __restrict__ sc, long
     xs.acquire();
     {
       const float* __restrict__ xp = xs.chunk(tc);
-      const f4 yv = xs.load(xp + k * CI_TC);
+      const f4 yv = xs.load(xp + k * xs.rs());
       float r0 = yv.x, r1 = yv.y, r2 = yv.z, r3 = yv.w;   // row k holds the centred series
 #pragma unroll 5
       for (int j = 0; j < k; ++j) {
         const float bj = sb[j * sbld];
-        const f4 x = xs.load(xp + j * CI_TC);
+        const f4 x = xs.load(xp + j * xs.rs());
         r0 = fmaf(-bj, x.x, r0); r1 = fmaf(-bj, x.y, r1);
         r2 = fmaf(-bj, x.z, r2); r3 = fmaf(-bj, x.w, r3);
       }
@@ -164,7 +166,7 @@ CI_HD void eval_lane(const float* u, long ld, const float* __restrict__ sc, long
         const float* __restrict__ xp = xs.chunk(tc);
 #pragma unroll 5
         for (int j = 0; j < k; ++j) {
-          const f4 x = xs.load(xp + j * CI_TC);
+          const f4 x = xs.load(xp + j * xs.rs());
           float a0 = sb[j * sbld], a1;
           a0 = fmaf(-rb0, x.x, a0); a1 = -rb1 * x.y;
           a0 = fmaf(-rb2, x.z, a0); a1 = fmaf(-rb3, x.w, a1);
@@ -239,7 +241,7 @@ struct EffLane {
   CI_HD void regress_fwd(int tc) {
     xs.acquire();
     const float* __restrict__ xp = xs.chunk(tc);
-    const f4 yv = xs.load(xp + k * CI_TC);
+    const f4 yv = xs.load(xp + k * xs.rs());
     pf2 r01 = mk2(yv.x, yv.y), r23 = mk2(yv.z, yv.w), s01 = mk2(0.f, 0.f), s23 = mk2(0.f, 0.f);
     const float* __restrict__ bp = sb;
     int j = 0;
@@ -251,7 +253,7 @@ struct EffLane {
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           nb[q] = bp[(h + q) * SBLD];
-          x[q] = xs.load(xp + (h + q) * CI_TC);
+          x[q] = xs.load(xp + (h + q) * xs.rs());
         }
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
@@ -265,7 +267,7 @@ struct EffLane {
         }
       }
       bp += 10 * SBLD;
-      xp += 10 * CI_TC;
+      xp += 10 * xs.rs();
     }
     for (; j < k; ++j) {
       const float nb = bp[0];
@@ -273,7 +275,7 @@ struct EffLane {
       r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
       r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
       bp += SBLD;
-      xp += CI_TC;
+      xp += xs.rs();
     }
     r01 = fadd2(r01, s01);
     r23 = fadd2(r23, s23);
@@ -296,7 +298,7 @@ struct EffLane {
           pf2 a[5];
 #pragma unroll
           for (int q = 0; q < 5; ++q) {
-            x[q] = xs.load(xp + (h + q) * CI_TC);
+            x[q] = xs.load(xp + (h + q) * xs.rs());
             a[q] = mk2(bp[(h + q) * SBLD], 0.f);
           }
 #pragma unroll
@@ -307,7 +309,7 @@ struct EffLane {
           }
         }
         bp += 10 * SBLD;
-        xp += 10 * CI_TC;
+        xp += 10 * xs.rs();
       }
       for (; j < k; ++j) {
         const f4 x = xs.load(xp);
@@ -316,7 +318,7 @@ struct EffLane {
         a = ffma2(mk2(x.z, x.w), n23, a);
         bp[0] = a.x + a.y;
         bp += SBLD;
-        xp += CI_TC;
+        xp += xs.rs();
       }
     }
     xs.release(tc - 1);

@@ -51,6 +51,9 @@ class DeviceBatch:
             self.X = torch.empty((self.Tpad // 4, self.N, self.k + 1, 4), dtype=torch.float32, device=self.device)
             nt.check(self.lib.ci_pack_design(ctypes.byref(L), nt.ptr(Xrm), nt.ptr(self.y), nt.ptr(self.sconst), nt.ptr(self.X),
                                              nt.stream_ptr()), 'ci_pack_design')
+            # covariate-major copy [Tpad/4][k+1][N][4] for calls with fewer than 4 lanes per series (one chain /
+            # one VI sample, the reference's defaults): built on first use, see data()
+            self.XT = None
             if Xrm is not None:
                 # stream-ordered: Xrm may be released once the pack kernel has been enqueued
                 Xrm.record_stream(torch.cuda.current_stream())
@@ -60,9 +63,19 @@ class DeviceBatch:
     def layout(self, G):
         return nt.CiLayout(self.N, int(G), self.T, self.Tf, self.k, self.S, self.r, self.Tpad, self.flags, self.S2, self.r2)
 
-    def data(self):
-        return nt.CiData(nt.ptr(self.y).value, nt.ptr(self.X).value,
-                         nt.ptr(self.sconst).value)
+    def data(self, G=None):
+        """ci_data for a call with G lanes per series; G < 4 adds the covariate-major design block."""
+        xt = None
+        if G is not None and G < 4 and self.k >= 1 and self.lib.ci_eval_uses_xt(ctypes.byref(self.layout(G))):
+            if self.XT is None:
+                L = self.layout(1)
+                self.XT = torch.empty((self.Tpad // 4, self.k + 1, self.N, 4), dtype=torch.float32, device=self.device)
+                with torch.cuda.device(self.device):
+                    nt.check(self.lib.ci_repack_design_cov(ctypes.byref(L), nt.ptr(self.X), nt.ptr(self.XT),
+                                                           nt.stream_ptr()), 'ci_repack_design_cov')
+            xt = self.XT
+        return nt.CiData(nt.ptr(self.y).value, nt.ptr(self.X).value, nt.ptr(self.sconst).value,
+                         nt.ptr(xt).value if xt is not None else None)
 
     def workspace(self, kind, nbytes):
         buf = self._ws.get(kind)
@@ -84,7 +97,7 @@ class DeviceBatch:
             grad = torch.empty_like(u)
         nbytes = self.lib.ci_eval_workspace_bytes(ctypes.byref(L))
         ws = self.workspace('eval', nbytes)
-        D = self.data()
+        D = self.data(B // self.N)
         with torch.cuda.device(self.device):
             nt.check(self.lib.ci_kalman_logp_grad(ctypes.byref(L), ctypes.byref(D), nt.ptr(u.contiguous()),
                                                   nt.ptr(logp), nt.ptr(grad), nt.ptr(ws),
@@ -108,7 +121,7 @@ class DeviceBatch:
         mu, rho = self._f32(self.P, U), self._f32(self.P, U)
         loss = self._f32(num_steps, U) if return_loss else None
         ws = self.workspace('fit', self.lib.ci_vi_workspace_bytes(ctypes.byref(L), ctypes.c_int32(units_per_series)))
-        D = self.data()
+        D = self.data(units_per_series * sample_size)
         self._call('ci_vi_fit', ctypes.byref(L), ctypes.byref(D), ctypes.c_int32(units_per_series),
                    ctypes.c_int32(sample_size), ctypes.c_int32(num_steps), ctypes.c_float(learning_rate),
                    ctypes.c_float(init_scale), ctypes.c_uint64(seed), nt.ptr(mu), nt.ptr(rho), nt.ptr(loss),
@@ -136,7 +149,7 @@ class DeviceBatch:
             draws = self._f32(max(num_results, 1), self.P, B)
         stats = self._f32(4, B)
         ws = self.workspace('fit', self.lib.ci_hmc_workspace_bytes(ctypes.byref(L)))
-        D = self.data()
+        D = self.data(B // self.N)
         self._call('ci_hmc_run', ctypes.byref(L), ctypes.byref(D), nt.ptr(u), nt.ptr(step0.contiguous()),
                    ctypes.c_int32(num_results), ctypes.c_int32(num_warmup), ctypes.c_int32(num_adapt),
                    ctypes.c_int32(num_leapfrog), ctypes.c_float(target_accept), ctypes.c_uint64(seed),
