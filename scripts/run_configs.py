@@ -54,6 +54,12 @@ if __name__ == '__main__':
     if '3' in which:
         run('configs[3] slice: 10k series x 365, nseasons=7, 50 covariates, HMC 8 chains x 100 draws', 10000, 365, 30,
             50, 7, 'hmc', chains=8, num_results=100, num_warmup=50, predictive_draws=10, niter=500, seed=1)
+    if 'd' in which:
+        # the reference's DEFAULT settings at scale: one chain / one VI sample per series (model.py:361-386)
+        run('defaults, VI: 10k series x 365, nseasons=7, 50 covariates, fit_method=vi (200 steps), 1000 samples', 10000,
+            365, 30, 50, 7, 'vi', niter=1000, seed=1)
+        run('defaults, HMC: 10k series x 365, nseasons=7, 50 covariates, 1 chain x (50 warm-up + 100 draws)', 10000,
+            365, 30, 50, 7, 'hmc', chains=1, num_results=100, num_warmup=50, niter=1000, seed=1)
     if '4' in which:
         run('configs[4]: 100 series x 10k steps, nseasons=52, VI + 1000-sample forecast', 100, 10000, 520, 0, 52, 'vi',
             niter=1000, seed=1)
