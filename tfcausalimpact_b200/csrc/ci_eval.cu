@@ -1,18 +1,24 @@
 // K1-K3: joint log-prob + gradient of the fixed-layout structural time-series model, ONE kernel:
-//   k_eval<S, STAGED>  -- thread per (series, chain[, sample]) lane; per lane (ci_eval_lane.cuh):
+//   k_eval<S, XM, EFF, SMALL>  -- thread per (series, chain[, sample]) lane; per lane (ci_eval_lane.cuh):
 //        u -> sigma^2's, beta (shared-memory column)                                [K3 forward]
-//        per 4-step chunk: r = y - mean - X beta from the TMA-staged chunk, 4 Kalman steps,
+//        per 4-step chunk: r = y - mean - X beta from the staged chunk, 4 Kalman steps,
 //        tape (g, v) -> HBM                                                          [K2 + K1 forward]
-//        reverse sweep with software-pipelined tape reads, beta_bar += rbar X per chunk
+//        reverse sweep with L2-prefetched tape reads, beta_bar += rbar X per chunk
 //        VJP through horseshoe / softplus / sqrt + priors -> grad                   [K1-K3 reverse]
-// Lanes are the fastest axis of every per-lane array ([P][B] parameters, [T][S+1][B] tape), so each
-// warp access is one 128 B line.  The design matrix (with y as its last row) is chunk-major
-// [N][Tpad/4][k+1][4]: the run a (series, chunk) needs is 16(k+1) contiguous bytes, fetched by ONE
-// cp.async.bulk (TMA) per series into the CTA's staging buffer and signalled on an mbarrier; the
-// copy of chunk c+1 is issued as soon as every lane has consumed chunk c and lands while the 4 filter
-// steps of chunk c run, so the regression loops never wait on HBM.  All C chains of a series sit in
-// the same CTA and read the staged chunk by shared-memory broadcast.  Mean, packed covariance and
-// their adjoints stay in registers for the whole evaluation; nothing but the tape is spilled to HBM.
+//        optional leapfrog kick / drift epilogue (HMC)
+// Lanes are the fastest axis of every per-lane array ([P][B] parameters, warp-blocked tape), so each warp
+// access is one 128 B line.  The design matrix (with the centred y as its last row) is chunk-major
+// [Tpad/4][N][k+1][4]; how a chunk reaches the lanes is the XM policy:
+//   XM = 1 (>= 4 lanes per series)  the series of a warp are adjacent, so the block it needs for one chunk is ONE
+//          contiguous run: one cp.async.bulk (TMA) per (warp, chunk) into the warp's staging buffer, signalled
+//          on a per-warp mbarrier; the copy of chunk c+1 is issued as soon as every lane of the warp has consumed
+//          chunk c and lands while its 4 filter steps run.  The chains of a series read it by broadcast.
+//   XM = 2 (< 4 lanes per series)   every lane stages its own series' chunk with cp.async from the
+//          covariate-major copy [Tpad/4][k+1][N][4] (a warp reads one contiguous run per covariate).
+//   XM = 0 direct loads (k < 4, or the XM = 2 slices do not fit in shared memory).
+// EFF selects the seasonal-effects formulation (ci_kalman_eff.cuh), SMALL the few-lanes instantiation without the
+// register cap.  Mean, packed covariance and their adjoints stay in registers for the whole evaluation; nothing
+// but the tape goes to HBM.
 //   k_params_forward / k_offsets -- u -> beta / offsets for the predictive path (ci_predict.cu).
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
