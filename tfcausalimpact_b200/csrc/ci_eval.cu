@@ -159,11 +159,12 @@ __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ gra
 // registers and one of them must host 5 of the 17 warps (5 x 32 x 104 > 16384).  Measured with
 // __maxnreg__: 104 / 112 / 120 registers -> 1.26 / 1.15 / 1.11 ms (second wave) against 0.87 ms at 96
 // (unconstrained, ptxas would take 192).
-// SMALL = true is the few-lanes instantiation (B <= CI_SMALL_LANES: at most about one warp per scheduler):
-// nothing hides latency there, so the register cap is lifted and ptxas schedules for ILP (166 registers, no
-// spills): 0.336 -> 0.301 ms per evaluation at 1000 series x 8 chains.  (Prefetching the next tape entry into
-// registers instead of L2 was measured too: 0.310 ms.)
-#define CI_SMALL_LANES (148 * 4 * 32)
+// SMALL = true is the instantiation without the register cap (164 registers, no spills, ptxas schedules for
+// ILP), used whenever all lanes still fit in ONE wave at 12 warps per SM (B <= 56,832): measured faster than the
+// 96-register kernel at every such size (1000 series x 8 chains 0.336 -> 0.301 ms, 2500 x 8: 0.572 -> 0.479,
+// 7000 x 8: 0.654 -> 0.579).  The 80,000 lanes of the headline workload need 17 warps per SM, i.e. 96 registers.
+// (Prefetching the next tape entry into registers instead of L2 was measured too: 0.310 ms at 1000 x 8.)
+#define CI_SMALL_LANES (148 * 12 * 32)
 // XM: 0 = lanes read their chunks directly, 1 = TMA-staged per warp from the series-major block (>= 4 lanes per
 // series), 2 = cp.async-staged per lane from the covariate-major block (< 4 lanes per series).
 template <int S, int XM, bool EFF, bool SMALL>
