@@ -40,20 +40,25 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // consumed the previous chunk (__syncwarp -- no CTA-wide barrier, warps never wait for each other).
 struct XStaged {
   const float* lane_x;   // this lane's series slice of the warp's staging buffer (shared memory)
-  uint32_t sx_addr;      // warp staging buffer, shared-space address
-  uint32_t bar;          // warp mbarrier, shared-space address
+  uint32_t bar;          // warp mbarrier, shared-space address; the copy descriptor sits 16 bytes behind it
   uint32_t parity;
-  uint32_t bytes;        // bytes per (warp, chunk) = series_in_warp * (k + 1) * CI_TC * 4
-  const float* gsrc;     // XY[0][first series of the warp] (global)
-  long cstride;          // floats between consecutive chunks = N * (k + 1) * CI_TC
-
+  // Copy descriptor in shared memory (written once per warp, read by lane 0 when it issues a copy), so that the
+  // warp-uniform copy parameters do not occupy registers in every lane for the whole kernel:
+  //   [bar + 16] global source of chunk 0 (8 bytes), [bar + 24] bytes per chunk, [bar + 28] staging buffer address,
+  //   [bar + 32] bytes between consecutive chunks (8 bytes)
   __device__ __forceinline__ void issue(int tc) const {   // lane 0 of the warp
+    uint64_t src, cbytes;
+    uint32_t bytes, sx_addr;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(src) : "r"(bar + 16));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bytes), "=r"(sx_addr) : "r"(bar + 24));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cbytes) : "r"(bar + 32));
+    src += (uint64_t)tc * cbytes;
     // (measured: dropping this proxy fence gains 0.2 % -- kept, the cross-proxy write-after-read stays explicit)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      sx_addr),
-                 "l"(gsrc + (long)tc * cstride), "r"(bytes), "r"(bar)
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
   }
   __device__ __forceinline__ void acquire() {
@@ -192,19 +197,20 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ XT, 
     if (bw0 >= B) return;                                 // whole warp is padding: nothing to wait for
     const int smax = staged_series_max(L.G);
     float* sx = smem + (4 + L.k) * EVAL_THREADS + (long)w * smax * stride;   // [smax][stride] per warp
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (4 + L.k) * EVAL_THREADS + (long)NW * smax * stride) + w;
+    // per warp: mbarrier (8 bytes, padded to 16) + 24-byte copy descriptor = 40 bytes, 16-byte aligned slots of 48
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(smem + (4 + L.k) * EVAL_THREADS + (long)NW * smax * stride) + w * 48;
     const int n_lo = (int)(bw0 / L.G);
     const long b_last = (bw0 + 31 < B ? bw0 + 31 : B - 1);
     const int ns = (int)(b_last / L.G) - n_lo + 1;
     XStaged xs;
     xs.lane_x = sx + (long)(n - n_lo) * stride;
-    xs.sx_addr = smem_u32(sx);
-    xs.bar = smem_u32(bar);
+    xs.bar = smem_u32(wbase);
     xs.parity = 0u;
-    xs.bytes = (uint32_t)ns * (uint32_t)stride * 4u;
-    xs.gsrc = XY + (long)n_lo * stride;
-    xs.cstride = cstride;
     if ((threadIdx.x & 31) == 0) {
+      *reinterpret_cast<uint64_t*>(wbase + 16) = reinterpret_cast<uint64_t>(XY + (long)n_lo * stride);
+      *reinterpret_cast<uint32_t*>(wbase + 24) = (uint32_t)ns * (uint32_t)stride * 4u;
+      *reinterpret_cast<uint32_t*>(wbase + 28) = smem_u32(sx);
+      *reinterpret_cast<uint64_t*>(wbase + 32) = (uint64_t)cstride * 4u;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs.bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -325,7 +331,7 @@ static int launch_eval_t(const ci_layout* L, const ci_data* D, const float* d_u,
                          const EvalWs& ws, cudaStream_t st, const LeapArgs& lf) {
   const long B = (long)L->N * L->G;
   size_t smem = (size_t)(4 + L->k) * EVAL_THREADS * sizeof(float);
-  if (XM == 1) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 8);
+  if (XM == 1) smem += (size_t)(EVAL_THREADS / 32) * (staged_series_max(L->G) * (L->k + 1) * CI_TC * sizeof(float) + 48);
   if (XM == 2) smem += (size_t)EVAL_THREADS * (L->k + 1) * CI_TC * sizeof(float);
   auto kern = k_eval<S, XM, EFF, SMALL>;
   if (smem > 48 * 1024) {
