@@ -160,6 +160,27 @@ __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ gra
   if (b < B) leap_epilogue(lf, P, B, b, grad);
 }
 
+// Lane index re-read from the special registers (volatile: not merged with the value computed at kernel entry),
+// so the pointers derived from it after the sweeps need no register during them.
+__device__ __forceinline__ long lane_index_reread() {
+  unsigned c, t;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(c));
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  return (long)c * 32 + t;
+}
+struct KernelLanePtrs {
+  const ci_layout& L;
+  const float* u;
+  const float* sconst;
+  float* logp;
+  float* grad;
+  __device__ __forceinline__ LanePtrs operator()() const {
+    const long b = lane_index_reread();
+    const int n = (int)(b / L.G);
+    return LanePtrs{u + b, sconst + n, logp + b, grad + b};
+  }
+};
+
 // 96 registers is the ceiling for 17 resident warps per SM: each of the 4 SM sub-partitions owns 16 K
 // registers and one of them must host 5 of the 17 warps (5 x 32 x 104 > 16384).  Measured with
 // __maxnreg__: 104 / 112 / 120 registers -> 1.26 / 1.15 / 1.11 ms (second wave) against 0.87 ms at 96
@@ -218,12 +239,12 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ XT, 
     if ((threadIdx.x & 31) == 0) xs.issue(0);
     if (valid) {
       if (EFF)
-        eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
-                                            logp + b, grad + b, pfrow);
+        eval_lane_eff<ES, 32, EVAL_THREADS>(KernelLanePtrs{L, u, sconst, logp, grad}, B, L.N, xs, L.T, L.k, sb, sr,
+                                            tape_eff, tstep_eff, pfrow);
       else
         eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b,
                      grad + b);
-      leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);
+      leap_epilogue(lf, num_params(L.k, L.S), (long)L.N * L.G, lane_index_reread(), grad);
     } else {
       idle_lane(xs, L.T);
     }
@@ -233,8 +254,8 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ XT, 
     XAsync xs{sx, smem_u32(sx), XT + (long)n * CI_TC, cstride, L.k + 1, L.N * CI_TC};
     xs.issue(0);
     if (EFF)
-      eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
-                                          logp + b, grad + b, pfrow);
+      eval_lane_eff<ES, 32, EVAL_THREADS>(KernelLanePtrs{L, u, sconst, logp, grad}, B, L.N, xs, L.T, L.k, sb, sr,
+                                          tape_eff, tstep_eff, pfrow);
     else
       eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
     leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);
@@ -242,8 +263,8 @@ k_eval(ci_layout L, const float* __restrict__ XY, const float* __restrict__ XT, 
     if (!valid) return;
     XDirect xs{XY + (long)n * stride, cstride};
     if (EFF)
-      eval_lane_eff<ES, 32, EVAL_THREADS>(u + b, B, sconst + n, L.N, xs, L.T, L.k, sb, sr, tape_eff, tstep_eff,
-                                          logp + b, grad + b, pfrow);
+      eval_lane_eff<ES, 32, EVAL_THREADS>(KernelLanePtrs{L, u, sconst, logp, grad}, B, L.N, xs, L.T, L.k, sb, sr,
+                                          tape_eff, tstep_eff, pfrow);
     else
       eval_lane<S>(u + b, B, sconst + n, L.N, xs, L.T, L.k, L.r, sb, EVAL_THREADS, sr, tape + b, B, logp + b, grad + b);
     leap_epilogue(lf, num_params(L.k, L.S), B, b, grad);

@@ -409,14 +409,30 @@ struct EffLane {
 // `tstep` floats apart (device: warp-blocked [T][warps][S+1][32], TQ = 32; host shim: TQ = 1); the
 // scratch column stride SBLD is a compile-time constant so the regression loops address shared
 // memory with immediates.
-template <int S, int TQ, int SBLD, class XS>
-CI_HD void eval_lane_eff(const float* u, long ld, const float* __restrict__ sc, long scld, XS& xs,
-                         int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
-                         int tstep, float* __restrict__ logp_out, float* __restrict__ grad, int pfrow = -1) {
-  const LaneScalars ls = params_forward_lane(u, ld, k, S, sc, scld, sb, SBLD, -1.0f);   // sb <- -beta
+// The lane's global pointers (u, constants, outputs) are obtained from `ptrs()` twice -- before the sweeps and again
+// after them -- instead of being passed in: on the device the functor re-derives them from the kernel parameters
+// and the (volatile-read) block / thread index, so none of them occupies a register during the T-step sweeps.
+struct LanePtrs {
+  const float* u;
+  const float* sc;
+  float* logp;
+  float* grad;
+};
+struct FixedLanePtrs {
+  LanePtrs p;
+  CI_HD LanePtrs operator()() const { return p; }
+};
+
+template <int S, int TQ, int SBLD, class XS, class PF>
+CI_HD void eval_lane_eff(const PF& ptrs, long ld, long scld, XS& xs, int T, int k, float* __restrict__ sb,
+                         float* __restrict__ sr, float* __restrict__ tape, int tstep, int pfrow = -1) {
   using LaneT = EffLane<S, XS, TQ, SBLD>;
+  float lp0;
+  const LanePtrs p0 = ptrs();
+  const LaneScalars ls = params_forward_lane(p0.u, ld, k, S, p0.sc, scld, sb, SBLD, -1.0f);   // sb <- -beta
+  lp0 = ls.lp0;
   LaneT L(xs, T, k, sb, sr, tape, tstep, ls.R, ls.ql, ls.qd, pfrow);
-  ef_init<S>(L.st, sc[SC_M0 * scld], sc[SC_P0 * scld]);
+  ef_init<S>(L.st, p0.sc[SC_M0 * scld], p0.sc[SC_P0 * scld]);
   L.forward();
   const float ll = -0.5f * (fmaf(L.acc, 0.6931471805599453f, L.quad) + (float)(T - L.nmask) * CI_LOG_2PI);
 
@@ -428,8 +444,18 @@ CI_HD void eval_lane_eff(const float* u, long ld, const float* __restrict__ sc, 
   sr[0] = 0.f; sr[1] = 0.f; sr[2] = 0.f; sr[3] = 0.f;
   L.tp -= tstep;  // entry of step T-1
   L.backward();
-  params_backward_lane(u, ld, k, S, sc, scld, sb, SBLD, L.Rb, L.qlb, L.qdb, grad);
-  *logp_out = ll + ls.lp0;
+  const LanePtrs p1 = ptrs();
+  params_backward_lane(p1.u, ld, k, S, p1.sc, scld, sb, SBLD, L.Rb, L.qlb, L.qdb, p1.grad);
+  *p1.logp = ll + lp0;
+}
+
+// pointer-argument form (host shim, tests)
+template <int S, int TQ, int SBLD, class XS>
+CI_HD void eval_lane_eff(const float* u, long ld, const float* __restrict__ sc, long scld, XS& xs,
+                         int T, int k, float* __restrict__ sb, float* __restrict__ sr, float* __restrict__ tape,
+                         int tstep, float* __restrict__ logp_out, float* __restrict__ grad, int pfrow = -1) {
+  const FixedLanePtrs pf{LanePtrs{u, sc, logp_out, grad}};
+  eval_lane_eff<S, TQ, SBLD>(pf, ld, scld, xs, T, k, sb, sr, tape, tstep, pfrow);
 }
 
 }  // namespace ci
