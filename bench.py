@@ -217,6 +217,9 @@ def main():
     assert torch.cuda.is_available(), 'bench.py (impl b200) needs a CUDA device; there is no CPU fallback'
     torch.cuda.set_device(local)
     dev = torch.device(f'cuda:{local}')
+    if world > 1:
+        from tfcausalimpact_b200.distributed import bind_to_gpu_numa
+        bind_to_gpu_numa(local)          # pinned host buffers of the e2e leg on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
