@@ -212,3 +212,43 @@ def test_edge_shapes_match_oracle(S, r, k, T, N, G, masked):
     np.testing.assert_allclose(pv.cpu().numpy().T, var_o.numpy(), rtol=1e-4)
     sims, mean = db.forecast_sample(ud, fs, 64, seed=1)
     assert torch.isfinite(sims).all() and torch.isfinite(mean).all()
+
+
+def _fuzz_cases(n=24, seed=2024):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        S = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 7, 7, 12, 9]))
+        r = int(rng.choice([1, 1, 1, 2, 3])) if S > 1 else 1
+        k = int(rng.choice([0, 1, 3, 4, 5, 9, 10, 17, 50]))
+        T = int(rng.integers(6, 70))
+        G = int(rng.choice([1, 2, 3, 4, 5, 8, 8, 12]))
+        N = int(rng.choice([1, 2, 5, 8, 9, 13, 33]))
+        nan_frac = float(rng.choice([0.0, 0.0, 0.1, 0.3]))
+        out.append((S, r, k, T, nan_frac, N, G))
+    return out
+
+
+@pytest.mark.parametrize('S,r,k,T,nan_frac,N,G', _fuzz_cases())
+def test_random_shapes_match_oracle(S, r, k, T, nan_frac, N, G):
+    """Seeded random layouts across every evaluation kernel and staging policy (direct / TMA per warp / cp.async
+    per lane, effects and residual basis, capped and uncapped registers, warp- and CTA-per-lane)."""
+    from tfcausalimpact_b200.engine import DeviceBatch
+    Tf = 5
+    L = O.Layout(T, Tf, k, S, r)
+    y, _, X = synth_problem(N, T, Tf, k, S, r, seed=S * 1000 + k * 10 + T, nan_frac=nan_frac)
+    prob = O.Problem.build(y, X, L, dtype=torch.float64)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S, season_duration=r)
+    rng = np.random.default_rng(T)
+    B = N * G
+    u = (rng.normal(size=(L.P, B)) * 0.6).astype(np.float32)
+    u[0] -= 1.0
+    u[1] -= 2.0
+    lp, g = db.logp_grad(torch.as_tensor(u).cuda())
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    series = torch.arange(B) // G
+    lpo, go = O.target_log_prob_and_grad(prob, torch.tensor(u.T.astype(np.float64)), series)
+    lpo, go = lpo.numpy(), go.numpy().T
+    np.testing.assert_allclose(lp, lpo, rtol=1e-4, atol=1e-4)
+    gmax = np.abs(go).max(axis=0, keepdims=True)
+    assert np.all(np.abs(g - go) <= 1e-4 * np.abs(go) + 2e-5 * gmax)
