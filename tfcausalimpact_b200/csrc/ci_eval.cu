@@ -300,34 +300,50 @@ __global__ void k_params_forward(ci_layout L, const float* __restrict__ sconst,
 
 // out[t - t_lo][b] for t in [t_lo, t_hi):  with_y ? y[n][t] - mean[n] - sum_j beta[j][b] X[n][j][t]
 //                                                 : mean[n] + sum_j beta[j][b] X[n][j][t];
-// one (lane, 4-step chunk) per thread.  Used by the predictive path only.
-__global__ void k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ XY,
-                          const float* __restrict__ sconst, const float* __restrict__ beta,
-                          float* __restrict__ out, int t_lo, int t_hi, int with_y) {
+// Used by the predictive path only.
+// A thread owns one lane and OFF_NCH consecutive chunks: beta_j is loaded once per covariate and re-used for
+// 4 OFF_NCH steps (one chunk per thread re-read the lane's whole beta column for every chunk: 18 GB of L2
+// traffic for 1 M lanes x 365 steps x 50 covariates).
+constexpr int OFF_NCH = 8;
+__global__ void __launch_bounds__(128)
+k_offsets(ci_layout L, const float* __restrict__ y, const float* __restrict__ XY,
+          const float* __restrict__ sconst, const float* __restrict__ beta,
+          float* __restrict__ out, int t_lo, int t_hi, int with_y) {
   const long B = (long)L.N * L.G;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = (int)(b / L.G);
-  const int tc = t_lo / CI_TC + blockIdx.y;
-  const int t0 = tc * CI_TC;
-  if (t0 >= t_hi) return;
+  const int tc0 = t_lo / CI_TC + blockIdx.y * OFF_NCH;
+  if (tc0 * CI_TC >= t_hi) return;
+  const int nch_tot = (t_hi + CI_TC - 1) / CI_TC;
   const float mean = sconst[SC_MEAN * L.N + n];
-  float a[CI_TC];
+  float a[OFF_NCH][CI_TC];
 #pragma unroll
-  for (int i = 0; i < CI_TC; ++i) a[i] = -mean;
+  for (int c = 0; c < OFF_NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < CI_TC; ++i) a[c][i] = -mean;
   const int stride = (L.k + 1) * CI_TC;
-  XDirect xs{XY + (long)n * stride, (long)L.N * stride};
-  const float* __restrict__ xp = xs.chunk(tc);
+  const long cstride = (long)L.N * stride;
+  const float* __restrict__ xp0 = XY + (long)n * stride + (long)tc0 * cstride;
   for (int j = 0; j < L.k; ++j) {
-    const float bj = beta[(long)j * B + b];
-    const f4 x = xs.load(xp + j * CI_TC);
-    a[0] = fmaf(-bj, x.x, a[0]); a[1] = fmaf(-bj, x.y, a[1]);
-    a[2] = fmaf(-bj, x.z, a[2]); a[3] = fmaf(-bj, x.w, a[3]);
+    const float nbj = -beta[(long)j * B + b];
+#pragma unroll
+    for (int c = 0; c < OFF_NCH; ++c) {
+      if (tc0 + c < nch_tot) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(xp0 + (long)c * cstride + j * CI_TC));
+        a[c][0] = fmaf(nbj, x.x, a[c][0]); a[c][1] = fmaf(nbj, x.y, a[c][1]);
+        a[c][2] = fmaf(nbj, x.z, a[c][2]); a[c][3] = fmaf(nbj, x.w, a[c][3]);
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < CI_TC; ++i) {
-    const int t = t0 + i;
-    if (t >= t_lo && t < t_hi) out[(long)(t - t_lo) * B + b] = with_y ? __ldg(y + (long)n * L.T + t) + a[i] : -a[i];
+  for (int c = 0; c < OFF_NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < CI_TC; ++i) {
+      const int t = (tc0 + c) * CI_TC + i;
+      if (t >= t_lo && t < t_hi)
+        out[(long)(t - t_lo) * B + b] = with_y ? __ldg(y + (long)n * L.T + t) + a[c][i] : -a[c][i];
+    }
   }
 }
 
@@ -338,7 +354,8 @@ void launch_offsets(const ci_layout* L, const ci_data* D, const float* beta, flo
   const unsigned gb = (unsigned)((B + bs - 1) / bs);
   const int chunks = (t_hi + CI_TC - 1) / CI_TC - t_lo / CI_TC;
   if (chunks <= 0) return;
-  k_offsets<<<dim3(gb, chunks), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo, t_hi, with_y);
+  k_offsets<<<dim3(gb, (chunks + OFF_NCH - 1) / OFF_NCH), bs, 0, st>>>(*L, D->d_y, D->d_X, D->d_sconst, beta, out, t_lo,
+                                                                      t_hi, with_y);
 }
 
 void launch_params_forward(const ci_layout* L, const ci_data* D, const float* d_u, float* beta, float* scal,
