@@ -891,6 +891,20 @@ k_eval_cta(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
   const float R = scal[0], ql = scal[1], qd = scal[2], lp0 = scal[3], qs = scal[4], qd2 = scal[5];
   const int stride = (k + 1) * CI_TC;
   float* rs = rscr + b * (long)(2 * T);       // [T] residuals, then [T] rbar
+  // Per-thread constants of the sweeps: this thread's rows i = ty + RG q (q < NQ) and column tx; membership of
+  // the seasonal blocks as 0/1 weights, so that the drift direction of a step is ONE compare + select per row
+  // (w_i = in-block ? (i == J ? 1 - S : 1) : 0).
+  constexpr int NQ = CTA_COLS / RG;
+  float in1[NQ], in2[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = ty + RG * q;
+    in1[q] = (S > 1 && i >= so && i < so + S && i < D) ? 1.f : 0.f;
+    in2[q] = (TWO && i >= so2 && i < so2 + S2 && i < D) ? 1.f : 0.f;
+  }
+  const float in1x = (S > 1 && tx >= so && tx < so + S) ? 1.f : 0.f;
+  const float in2x = (TWO && tx >= so2 && tx < so2 + S2) ? 1.f : 0.f;
+  const float wJ = (float)(1 - S), wJ2 = (float)(1 - S2);
   // ---- pre-pass: residuals ---------------------------------------------------------------------------
   for (int t = tid; t < T; t += NT) {
     const float* xp = XY + ((long)(t / CI_TC) * L.N + n) * stride + (t % CI_TC);
@@ -949,14 +963,17 @@ k_eval_cta(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     if (col_ok) {
       if (ty == 0 && obs) m[tx] = fmaf(gj, v * is, m[tx]);
       const float gx = g[tx];
-      const float wx = drift_w(tx, z.c, S, so), w2x = TWO ? drift_w(tx, z.c2, S2, so2) : 0.f;
-#pragma unroll 4
-      for (int i = ty; i < D; i += RG) {
-        float nv = fmaf(qq * drift_w(i, z.c, S, so), wx, fmaf(g[i] * nis, gx, P[i * D + tx]));
-        if (TWO) nv = fmaf(qq2 * drift_w(i, z.c2, S2, so2), w2x, nv);
-        if (so != 2 && i == 0 && tx == 0) nv += ql;     // level variance (LocalLinearTrend: after F P F^T below)
-        P[i * D + tx] = nv;
+      const float qwx = qq * (tx == J ? wJ : in1x), qw2x = TWO ? qq2 * (tx == J2 ? wJ2 : in2x) : 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int i = ty + RG * q;
+        if (i < D) {
+          float nv = fmaf(i == J ? wJ : in1[q], qwx, fmaf(g[i] * nis, gx, P[i * D + tx]));
+          if (TWO) nv = fmaf(i == J2 ? wJ2 : in2[q], qw2x, nv);
+          P[i * D + tx] = nv;
+        }
       }
+      if (so != 2 && tid == 0) P[0] += ql;     // level variance (LocalLinearTrend: after F P F^T below)
       if (ty == RG - 1) tp[(long)t * (D + 1) + tx] = gx;
     }
     if (tid == NT - 1) tp[(long)t * (D + 1) + D] = obs ? v : __int_as_float(0x7fc00000);
@@ -1011,12 +1028,15 @@ k_eval_cta(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
     {
       float c0 = 0.f, c1 = 0.f, c2 = 0.f;
       if (col_ok && (obs || z.change || z.change2)) {
-#pragma unroll 4
-        for (int i = ty; i < D; i += RG) {
-          const float pb = Pb[i * D + tx];
-          c0 = fmaf(pb, g[i], c0);
-          c1 = fmaf(pb, drift_w(i, z.c, S, so), c1);
-          if (TWO) c2 = fmaf(pb, drift_w(i, z.c2, S2, so2), c2);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int i = ty + RG * q;
+          if (i < D) {
+            const float pb = Pb[i * D + tx];
+            c0 = fmaf(pb, g[i], c0);
+            c1 = fmaf(pb, i == J ? wJ : in1[q], c1);
+            if (TWO) c2 = fmaf(pb, i == J2 ? wJ2 : in2[q], c2);
+          }
         }
       }
       part[(0 * RG + ty) * CTA_COLS + tx] = c0;
@@ -1033,8 +1053,8 @@ k_eval_cta(ci_layout L, const float* __restrict__ XY, const float* __restrict__ 
         nac += part[(1 * RG + q) * CTA_COLS + tx];
         nac2 += part[(2 * RG + q) * CTA_COLS + tx];
       }
-      const float wx = col_ok ? drift_w(tx, z.c, S, so) : 0.f;
-      const float w2x = (TWO && col_ok) ? drift_w(tx, z.c2, S2, so2) : 0.f;
+      const float wx = col_ok ? (tx == J ? wJ : in1x) : 0.f;
+      const float w2x = (TWO && col_ok) ? (tx == J2 ? wJ2 : in2x) : 0.f;
       const float pa = col_ok ? mb[tx] * gx : 0.f;
       const float pg = gx * col;
       const float s0 = warp_sum(pa), s1 = warp_sum(pg), s2 = warp_sum(wx * nac), s3 = warp_sum(w2x * nac2);
