@@ -35,8 +35,9 @@ extern "C" {
 
 #define CI_SCONST_FIELDS 8
 
-/* Fixed state-space layout of Sum([LocalLevel, SparseLinearRegression?, Seasonal?]) as built by
- * causalimpact/model.py:239-321 (`build_default_model`). */
+/* Fixed state-space layout of Sum([LocalLevel | LocalLinearTrend, SparseLinearRegression | LinearRegression ?,
+ * Seasonal?, Seasonal?]): flags == 0 and S2 <= 1 is the default model built by causalimpact/model.py:239-321
+ * (`build_default_model`); `flags`, `S2`, `r2` describe the custom `model=` set (main.py:186-252 examples). */
 typedef struct ci_layout {
   int32_t N;    /* series in this call */
   int32_t G;    /* lanes per series (chains x Monte-Carlo samples); B = N * G */
@@ -111,6 +112,13 @@ int ci_repack_design_cov(const ci_layout* L, const float* d_XY_packed, float* d_
 size_t ci_eval_workspace_bytes(const ci_layout* L);
 int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp,
                         float* d_grad, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Tuning hook (process-wide, not part of the reference-facing contract; used by bench / A-B scripts):
+ *   "coop_threads_per_lane"  8 (default), 4, 2, or 0 = never use the lane-cooperative evaluation kernel
+ *   "coop_max_lanes"         largest N * G served by it (-1 = default: one resident wave)
+ * The lane-cooperative kernel (csrc/ci_eval_coop.cu) serves default-model layouts with 2 <= nseasons <= 7,
+ * season_duration 1, whose lanes cannot fill the GPU at one thread per lane. */
+int ci_set_option(const char* name, long value);
 
 /* ---- K5: mean-field ADVI ---------------------------------------------------------------------
  * Replaces: tfp.sts.build_factored_surrogate_posterior + tfp.vi.fit_surrogate_posterior with

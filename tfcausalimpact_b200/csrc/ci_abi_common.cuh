@@ -83,13 +83,22 @@ int launch_forecast_moments_big(const ci_layout* L, const float* fs, const float
 void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
                          const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t stream);
 
+// ---- lane-cooperative evaluation for sub-wave batches, ci_eval_coop.cu -----------------------------
+bool coop_eligible(const ci_layout* L);         // layout + lane count served by the cooperative kernel
+size_t coop_tape_floats(const ci_layout* L);    // [T][lanes padded to 16][8]
+void coop_set_option(int tpl, long max_lanes);  // tuning hook behind ci_set_option
+struct LeapArgs;
+int launch_eval_coop(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                     float* tape, cudaStream_t stream, const LeapArgs& lf);
+
 // Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
   float* tape;   // [T][S+1][B] (g_0..g_{S-1}, v), or warp-blocked [T][B/32][S+1][32] (effects path)
 };
 inline size_t eval_ws_floats(const ci_layout* L, EvalWs* ws, Carver* c) {
   const size_t B = ((size_t)L->N * L->G + 31) / 32 * 32;   // whole warps (warp-blocked tape layout)
-  const size_t nt = ci_reg_path(L) ? (size_t)L->T * (L->S + 1) * B : big_tape_floats(L);
+  size_t nt = ci_reg_path(L) ? (size_t)L->T * (L->S + 1) * B : big_tape_floats(L);
+  if (ci_reg_path(L) && L->r == 1 && L->S >= 2 && L->S <= 7 && coop_tape_floats(L) > nt) nt = coop_tape_floats(L);
   if (ws && c) ws->tape = c->floats(nt);
   return align_up(nt * 4, 256);
 }

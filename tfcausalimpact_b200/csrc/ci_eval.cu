@@ -20,8 +20,10 @@
 // register cap.  Mean, packed covariance and their adjoints stay in registers for the whole evaluation; nothing
 // but the tape goes to HBM.
 //   k_params_forward / k_offsets -- u -> beta / offsets for the predictive path (ci_predict.cu).
+#include <cstring>
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
+#include "ci_xstage.cuh"
 
 namespace ci {
 
@@ -31,58 +33,6 @@ char* last_error_buf() {
 }
 
 constexpr int EVAL_THREADS = 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// TMA-staged policy: every WARP owns a staging buffer + mbarrier.  The series its 32 lanes belong to
-// are adjacent, so with the [chunk][series][k+1][4] layout the run it needs for one chunk is a single
-// contiguous block: ONE cp.async.bulk per (warp, chunk), issued by lane 0 as soon as the warp has
-// consumed the previous chunk (__syncwarp -- no CTA-wide barrier, warps never wait for each other).
-struct XStaged {
-  const float* lane_x;   // this lane's series slice of the warp's staging buffer (shared memory)
-  uint32_t bar;          // warp mbarrier, shared-space address; the copy descriptor sits 16 bytes behind it
-  uint32_t parity;
-  // Copy descriptor in shared memory (written once per warp, read by lane 0 when it issues a copy), so that the
-  // warp-uniform copy parameters do not occupy registers in every lane for the whole kernel:
-  //   [bar + 16] global source of chunk 0 (8 bytes), [bar + 24] bytes per chunk, [bar + 28] staging buffer address,
-  //   [bar + 32] bytes between consecutive chunks (8 bytes)
-  __device__ __forceinline__ void issue(int tc) const {   // lane 0 of the warp
-    uint64_t src, cbytes;
-    uint32_t bytes, sx_addr;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(src) : "r"(bar + 16));
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bytes), "=r"(sx_addr) : "r"(bar + 24));
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cbytes) : "r"(bar + 32));
-    src += (uint64_t)tc * cbytes;
-    // (measured: dropping this proxy fence gains 0.2 % -- kept, the cross-proxy write-after-read stays explicit)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     sx_addr),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-  }
-  __device__ __forceinline__ void acquire() {
-    uint32_t ok;
-    do {
-      asm volatile(
-          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-          : "=r"(ok)
-          : "r"(bar), "r"(parity)
-          : "memory");
-    } while (!ok);
-    parity ^= 1u;
-  }
-  __device__ __forceinline__ void release(int next_tc) const {
-    __syncwarp();   // every lane of the warp (padding lanes included) has consumed the staged chunk
-    if ((threadIdx.x & 31) == 0 && next_tc >= 0) issue(next_tc);
-  }
-  __device__ __forceinline__ const float* chunk(int) const { return lane_x; }
-  __device__ __forceinline__ constexpr int rs() const { return CI_TC; }
-  __device__ __forceinline__ f4 load(const float* p) const {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    return f4{v.x, v.y, v.z, v.w};
-  }
-};
 
 // Few lanes per series (G < 4: one chain / one VI sample per series, the reference's defaults): every lane copies
 // ITS OWN series' chunk -- k + 1 rows of 16 bytes -- from the covariate-major block XT [chunk][k+1][N][4] into a
@@ -410,6 +360,7 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
     CI_CHECK_LAUNCH();
     return CI_OK;
   }
+  if (coop_eligible(L)) return launch_eval_coop(L, D, d_u, d_logp, d_grad, ws.tape, st, lf);
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   const bool small = eff && (long)L->N * L->G <= CI_SMALL_LANES;
 #define CI_EFF_S(S_) (S_ >= 2 && S_ <= CI_MAX_EFF_S)
@@ -590,6 +541,22 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
   EvalWs ws;
   eval_ws_floats(L, &ws, &c);
   return launch_eval(L, D, d_u, d_logp, d_grad, ws, (cudaStream_t)stream);
+}
+
+int ci_set_option(const char* name, long value) {
+  CI_CHECK_ARG(name, "NULL option name");
+  static int tpl = 8;
+  static long max_lanes = -1;
+  if (!strcmp(name, "coop_threads_per_lane")) {
+    CI_CHECK_ARG(value == 0 || value == 2 || value == 4 || value == 8, "coop_threads_per_lane must be 0, 2, 4 or 8");
+    tpl = (int)value;
+  } else if (!strcmp(name, "coop_max_lanes")) {
+    max_lanes = value;
+  } else {
+    return fail(CI_ERR_INVALID_ARGUMENT, "unknown option %s", name);
+  }
+  coop_set_option(tpl, max_lanes);
+  return CI_OK;
 }
 
 int ci_constrain(const ci_layout* L, const ci_data* D, const float* d_u, float* d_theta, void* stream) {
