@@ -545,10 +545,10 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
 
 int ci_set_option(const char* name, long value) {
   CI_CHECK_ARG(name, "NULL option name");
-  static int tpl = 8;
+  static int tpl = -1;
   static long max_lanes = -1;
   if (!strcmp(name, "coop_threads_per_lane")) {
-    CI_CHECK_ARG(value == 0 || value == 2 || value == 4 || value == 8, "coop_threads_per_lane must be 0, 2, 4 or 8");
+    CI_CHECK_ARG(value == -1 || value == 0 || value == 4 || value == 8, "coop_threads_per_lane must be -1, 0, 4 or 8");
     tpl = (int)value;
   } else if (!strcmp(name, "coop_max_lanes")) {
     max_lanes = value;

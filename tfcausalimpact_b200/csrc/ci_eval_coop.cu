@@ -1,29 +1,43 @@
 // K1-K3 for SUB-WAVE batches: lane-cooperative joint log-prob + gradient evaluation.
 //
 // The thread-per-lane kernel (ci_eval.cu) fills the machine only when there are >= ~57k lanes; below that a lane
-// is one thread walking 2 T dependent steps and the SMs idle (10k lanes: 2 warps per SM).  Here TPL threads
-// (8, 4 or 2) share ONE (series, chain) lane of the seasonal-effects formulation (ci_kalman_eff.cuh: x = [level |
-// e_0 .. e_{S-1}], D = S + 1 <= 8, H_t = e_0 + e_{1+c}, F = I):
-//   * row-distributed covariance: sub-thread `sub` owns rows sub, sub + TPL, .. of the FULL D x D matrix P (and of
-//     its adjoint W); the mean m and its adjoint are replicated in every sub-thread
-//   * forward step: g_i = P[i][0] + P[i][J] is local, the D values are all-gathered with D width-TPL shuffles, the
-//     rank-1 update P[i][:] -= g_i g / s and the time update are row-local
-//   * reverse step: W g is row-local, the D values are all-gathered, everything else (g^T W g, sbar, gbar) is
-//     replicated arithmetic; the symmetric update W += sym(gbar H^T) touches columns 0 / J of every row and the
-//     whole rows 0 / J.  The quadratic forms of the Q adjoint are carried per row and reduced once at the end.
-//   * masked (missing) steps are branch-free (gain forced to 0), so a warp never diverges and every shuffle uses
-//     the full mask
-//   * regression: the k covariates are split over the TPL sub-threads (-beta / beta_bar slices in shared memory,
-//     X chunk TMA-staged per warp exactly as in ci_eval.cu), partial residuals combined by a butterfly
-//   * parameter transforms and their VJP (ci_params.cuh arithmetic) are split the same way; the HMC leapfrog
-//     kick / drift is applied by the sub-thread that produced the gradient component.
-// Tape: [T][warps][lanes per warp][8] = g_0 .. g_{S-1}, v (NaN = masked) per lane and step -- one 128 B line per
-// warp and step for TPL = 8.
+// is one thread walking 2 T dependent steps and the SMs idle (10k lanes: 2 warps per SM).  Here TPL threads (8 or
+// 4) share ONE (series, chain) lane of the seasonal-effects formulation (ci_kalman_eff.cuh: x = [level |
+// e_0 .. e_{S-1}], D = S + 1 <= 8, H_t = e_0 + e_{1+c}, F = I).  One warp = one CTA = 32 / TPL lanes.
+//
+// The evaluation is FOUR passes over the series, so that the dependent Kalman chains contain nothing else:
+//   1. residual pass   r_t = y_t - mean - X_t . beta for all t -> shared memory (covariates split over the TPL
+//                      sub-threads, -beta slices in registers, X chunks TMA-staged two deep, partial sums combined
+//                      by a recursive-halving butterfly: 4 shuffles per 4 steps at TPL = 8)
+//   2. forward filter  sub-thread `sub` owns rows sub * RPT .. of the FULL D x D covariance P as FP32x2 pairs; the
+//                      mean is replicated.  Per step: g_i = P[i][0] + P[i][J] is row-local, the 8 values are
+//                      all-gathered (shared-memory exchange: 1 store + 2 x 16-byte loads), the rank-1
+//                      update and the time update are row-local FFMA2 / FADD2.  The time loop is unrolled over the
+//                      season cycle, so every register index is static and there is no per-step dispatch.
+//                      Tape: g_0 .. g_7 per lane and step = exactly the row of the exchange buffer.  The rows of one
+//                      season cycle form a block of a shared-memory ring that ONE bulk (TMA) store per cycle writes to
+//                      the warp's contiguous tape [warp][T][8 x lanes]; the innovation v_t replaces r_t in shared memory
+//                      (NaN = masked step).
+//   3. reverse sweep   rows of the symmetric adjoint W = Pbar distributed the same way, mean adjoint replicated;
+//                      W g is row-local, all-gathered; g^T W g, sbar, gbar are replicated pair arithmetic; the
+//                      update W += sym(gbar H^T) touches columns 0 / J of every row and the whole rows 0 / J.
+//                      The tape streams back by bulk (TMA) loads three season cycles ahead of the sweep, so no global
+//                      load sits in the dependent chain.  dL/dr_t replaces v_t in shared memory.  The Q adjoint is
+//                      accumulated per row, reduced once.
+//   4. beta_bar pass   beta_bar_j = -sum_t rbar_t X_tj, second streaming pass over the TMA-staged chunks with
+//                      register accumulators, then the VJP through the parameter transforms (ci_params.cuh
+//                      arithmetic, covariates split over the sub-threads) and the fused HMC leapfrog kick / drift.
+// Masked (missing) steps are branch-free (gain forced to 0), so a warp never diverges.
 // Same math and the same parity tests as the thread-per-lane kernel; replaces the
 // arithmetic behind /root/reference/causalimpact/model.py:361-364,375-377 for small batches.
+#include <type_traits>
 #include "ci_abi_common.cuh"
 #include "ci_xstage.cuh"
 #include "ci_kalman_eff.cuh"
+
+// lane counts served by the cooperative kernel (measured crossovers, scripts/ab_coop.py; B200, k = 50, S = 7)
+#define CI_COOP_TPL8_LANES 12000L   // up to here 8 sub-threads per lane, above 4
+#define CI_COOP_MAX_LANES 24000L    // above: thread-per-lane kernel
 
 namespace ci {
 
@@ -31,6 +45,11 @@ namespace ci {
 __host__ __device__ inline int coop_series_max(int G, int lpw) {
   const int a = (lpw + G - 2) / G + 1;
   return a < lpw ? a : lpw;
+}
+// floats per lane of the shared-memory residual row: whole chunks, rows of a warp's lanes on distinct banks
+__host__ __device__ inline int coop_row_floats(int T, int lpw) {
+  const int nchunk = (T + CI_TC - 1) / CI_TC;
+  return (nchunk * CI_TC + 31) / 32 * 32 + 32 / lpw;
 }
 
 template <int TPL>
@@ -40,185 +59,260 @@ __device__ __forceinline__ float group_sum(float x) {
   return x;
 }
 
+template <int J>
+__device__ __forceinline__ float& el(pf2 (&a)[4]) {
+  if constexpr (J & 1) return a[J >> 1].y;
+  else return a[J >> 1].x;
+}
+template <int J>
+__device__ __forceinline__ float elc(const pf2 (&a)[4]) {
+  if constexpr (J & 1) return a[J >> 1].y;
+  else return a[J >> 1].x;
+}
+__device__ __forceinline__ float dot8(const pf2 (&a)[4], const pf2 (&b)[4]) {
+  pf2 t0 = fmul2(a[0], b[0]), t1 = fmul2(a[1], b[1]);
+  t0 = ffma2(a[2], b[2], t0);
+  t1 = ffma2(a[3], b[3], t1);
+  t0 = fadd2(t0, t1);
+  return t0.x + t0.y;
+}
+
 template <int S, int TPL>
 struct CoopLane {
   static constexpr int D = S + 1;
-  static constexpr int RPT = 8 / TPL;   // row slots per sub-thread (row = sub + TPL * q; rows >= D are empty)
+  static constexpr int RPT = 8 / TPL;   // rows per sub-thread: row = sub * RPT + q (rows >= D stay zero)
   static constexpr int LPW = 32 / TPL;
   const int sub;
-  const float R, ql, q11, q1c, qcc;
-  float m[D];          // forward: mean (replicated);  reverse: its adjoint (replicated)
+  const float R;
+  pf2 m[4];            // forward: mean (replicated);  reverse: its adjoint (replicated)
+  pf2 P[RPT][4];       // forward: own rows of P;  reverse: own rows of W = Pbar
   float ml[RPT];       // reverse: the adjoint mean at this sub-thread's own rows
-  float P[RPT][D];     // forward: own rows of P;  reverse: own rows of W = Pbar
-  float rs[RPT];       // reverse: sum_{j >= 1} W[row][j]
+  // per-row constants of the time update / its adjoint
+  float ql0[RPT], c0[RPT], c1[RPT], c2[RPT], r0m[RPT], sm1[RPT], smJ[RPT];
   float acc = 0.f, quad = 0.f;
   int nmask = 0;
   float Rb = 0.f, qlacc = 0.f, qdacc = 0.f;
 
-  __device__ __forceinline__ CoopLane(int sub_, float R_, float ql_, float qd_)
-      : sub(sub_), R(R_), ql(ql_), q11(qd_), q1c(-(float)(S - 1) * qd_), qcc((float)((S - 1) * (S - 1)) * qd_) {}
+  __device__ __forceinline__ CoopLane(int sub_, float R_, float ql, float qd) : sub(sub_), R(R_) {
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int row = sub * RPT + q;
+      const bool seas = row >= 1 && row < D;
+      ql0[q] = row == 0 ? ql : 0.f;
+      c0[q] = seas ? qd : 0.f;                                   // Q[i][j], i, j != J
+      c1[q] = seas ? -(float)(S - 1) * qd : 0.f;                 // Q[i][J] / Q[J][j]
+      c2[q] = seas ? (float)((S - 1) * (S - 1)) * qd : 0.f;      // Q[J][J]
+      r0m[q] = row == 0 ? 1.f : 0.f;
+      sm1[q] = seas ? 1.f : 0.f;
+      smJ[q] = seas ? -(float)(S - 1) : 0.f;
+    }
+  }
 
   __device__ __forceinline__ void init_forward(float m0, float p0) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) m[j] = 0.f;
-    m[0] = m0;
+    for (int p = 0; p < 4; ++p) m[p] = mk2(0.f, 0.f);
+    m[0].x = m0;
     const float off = -p0 * (1.0f / S);
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      const int row = sub + TPL * q;
+      const int row = sub * RPT + q;
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        float v = 0.f;
-        if (row == 0) v = (j == 0) ? p0 : 0.f;
-        else if (row < D) v = (j == 0) ? 0.f : ((j == row) ? p0 + off : off);
-        P[q][j] = v;
+      for (int j = 0; j < 8; ++j) {
+        float x = 0.f;
+        if (j < D) {
+          if (row == 0) x = (j == 0) ? p0 : 0.f;
+          else if (row < D) x = (j == 0) ? 0.f : ((j == row) ? p0 + off : off);
+        }
+        v[j] = x;
       }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) P[q][p] = mk2(v[2 * p], v[2 * p + 1]);
     }
   }
   __device__ __forceinline__ void init_reverse() {
 #pragma unroll
-    for (int j = 0; j < D; ++j) m[j] = 0.f;
+    for (int p = 0; p < 4; ++p) m[p] = mk2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       ml[q] = 0.f;
-      rs[q] = 0.f;
 #pragma unroll
-      for (int j = 0; j < D; ++j) P[q][j] = 0.f;
+      for (int p = 0; p < 4; ++p) P[q][p] = mk2(0.f, 0.f);
     }
   }
 
-  // measurement + time update at season C; writes this lane's tape entry (tp = the lane's 8-float slot)
+  // all-gather of one value per row through the lane's 8-float exchange row xb: out[j] = the value of row j.
+  // The caller alternates rows (or separates reuse by a __syncwarp), so one warp barrier per exchange suffices.
+  __device__ __forceinline__ void gather(const float (&loc)[RPT], pf2 (&out)[4], float* __restrict__ xb) {
+    if constexpr (RPT == 1) xb[sub] = loc[0];
+    else if constexpr (RPT == 2) *reinterpret_cast<float2*>(xb + 2 * sub) = make_float2(loc[0], loc[1]);
+    else *reinterpret_cast<float4*>(xb + 4 * sub) = make_float4(loc[0], loc[1], loc[2], loc[3]);
+    __syncwarp();
+    const float4 a = *reinterpret_cast<const float4*>(xb), b = *reinterpret_cast<const float4*>(xb + 4);
+    out[0] = mk2(a.x, a.y);
+    out[1] = mk2(a.z, a.w);
+    out[2] = mk2(b.x, b.y);
+    out[3] = mk2(b.z, b.w);
+  }
+
+  // measurement + time update at season C.  r = residual (NaN = masked); xb = the lane's row of the tape ring (the
+  // all-gathered gains ARE the tape entry); returns what replaces r_t in shared memory (v_t, NaN kept if masked)
   template <int C>
-  __device__ __forceinline__ void fwd(float r, float* __restrict__ tp) {
+  __device__ __forceinline__ float fwd(float r, float* __restrict__ xb) {
     constexpr int J = 1 + C;
     float gl[RPT];
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) gl[q] = P[q][0] + P[q][J];
-    float g[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) g[j] = __shfl_sync(0xffffffffu, gl[j / TPL], j % TPL, TPL);
+    for (int q = 0; q < RPT; ++q) gl[q] = elc<0>(P[q]) + elc<J>(P[q]);
+    pf2 g[4];
+    gather(gl, g, xb);
     const bool obs = (r == r);
-    const float s = g[0] + g[J] + R;
-    const float v = obs ? r - m[0] - m[J] : 0.f;
+    const float s = elc<0>(g) + elc<J>(g) + R;
+    const float v = obs ? r - elc<0>(m) - elc<J>(m) : 0.f;
     const float is = obs ? rcp(s) : 0.f;
     const float vis = v * is;
+    const pf2 vv = mk2(vis, vis);
 #pragma unroll
-    for (int j = 0; j < D; ++j) m[j] = fmaf(g[j], vis, m[j]);
+    for (int p = 0; p < 4; ++p) m[p] = ffma2(g[p], vv, m[p]);
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      const int row = sub + TPL * q;
-      const float ki = gl[q] * is;
-#pragma unroll
-      for (int j = 0; j < D; ++j) P[q][j] = fmaf(-ki, g[j], P[q][j]);
-      // tape slot `row`: g_row for row < S, v (NaN marks a masked step) at slot S
-      if (row <= S) tp[row] = (row == S) ? (obs ? v : r) : gl[q];
-      // time update P += diag(ql, qd w w^T), w = 1 - S e_C  (row-local)
-      const bool seas = row >= 1 && row < D;
+      const int row = sub * RPT + q;
+      const float ki = -gl[q] * is;
+      const pf2 kk = mk2(ki, ki);
+      // time update P += diag(ql, qd w w^T), w = 1 - S e_C, folded into the rank-1 update's addend
       const bool isj = row == J;
-      const float qa = seas ? (isj ? q1c : q11) : 0.f;
-      const float qb = seas ? (isj ? qcc : q1c) : 0.f;
-      P[q][0] += (row == 0) ? ql : 0.f;
+      const float qa = isj ? c1[q] : c0[q];
+      const float qb = isj ? c2[q] : c1[q];
+      float a[8];
 #pragma unroll
-      for (int j = 1; j < D; ++j) P[q][j] += (j == J) ? qb : qa;
+      for (int j = 0; j < 8; ++j) a[j] = (j == 0) ? ql0[q] : (j >= D ? 0.f : (j == J ? qb : qa));
+#pragma unroll
+      for (int p = 0; p < 4; ++p) P[q][p] = fadd2(ffma2(kk, g[p], P[q][p]), mk2(a[2 * p], a[2 * p + 1]));
     }
     acc += obs ? fast_log2(s) : 0.f;
     quad = fmaf(vis, v, quad);
     nmask += obs ? 0 : 1;
+    return obs ? v : r;
   }
 
-  // adjoint of the step at season C given the taped entry `e` (8 floats); returns rbar = dL/dr_t
+  // adjoint of the step at season C given the taped gains g (8 floats) and innovation; returns rbar = dL/dr_t
   template <int C>
-  __device__ __forceinline__ float bwd(const float (&e)[8]) {
+  __device__ __forceinline__ float bwd(const float4& ea, const float4& eb, float vraw, float* __restrict__ xb) {
     constexpr int J = 1 + C;
-    float g[D];
-    float gs = 0.f;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-      g[j] = e[j];
-      if (j >= 1) gs += e[j];
-    }
-    g[S] = -gs;   // the seasonal part of every covariance column sums to zero
-    const float vraw = e[S];
+    pf2 g[4] = {mk2(ea.x, ea.y), mk2(ea.z, ea.w), mk2(eb.x, eb.y), mk2(eb.z, eb.w)};
     const bool obs = (vraw == vraw);
     const float v = obs ? vraw : 0.f;
-    // adjoint of the time update (W before this step's measurement adjoint)
+    // adjoint of the time update (W before this step's measurement adjoint): ql += W[0][0], qd += w^T W w
+    pf2 wc[4];
+    {
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = (j == 0 || j >= D) ? 0.f : (j == J ? -(float)(S - 1) : 1.f);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) wc[p] = mk2(w[2 * p], w[2 * p + 1]);
+    }
+    float Wgl[RPT];
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      const int row = sub + TPL * q;
-      qlacc += (row == 0) ? P[q][0] : 0.f;
-      const bool seas = row >= 1 && row < D;
-      qdacc += seas ? rs[q] : 0.f;
-      qdacc += (row == J) ? fmaf((float)(S * S), P[q][J], -(2.f * S) * rs[q]) : 0.f;
+      const int row = sub * RPT + q;
+      qlacc = fmaf(r0m[q], elc<0>(P[q]), qlacc);
+      const float t = dot8(P[q], wc);
+      qdacc = fmaf(row == J ? smJ[q] : sm1[q], t, qdacc);
+      Wgl[q] = dot8(P[q], g);
     }
-    const float s = g[0] + g[J] + R;
+    const float s = elc<0>(g) + elc<J>(g) + R;
     const float is = obs ? rcp(s) : 0.f;
-    float a = 0.f;
-#pragma unroll
-    for (int j = 0; j < D; ++j) a = fmaf(m[j], g[j], a);
-    float Pgl[RPT];
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      float t = 0.f;
-#pragma unroll
-      for (int j = 0; j < D; ++j) t = fmaf(P[q][j], g[j], t);
-      Pgl[q] = t;
-    }
-    float Pg[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) Pg[j] = __shfl_sync(0xffffffffu, Pgl[j / TPL], j % TPL, TPL);
-    float gPg = 0.f;
-#pragma unroll
-    for (int j = 0; j < D; ++j) gPg = fmaf(g[j], Pg[j], gPg);
+    const float a = dot8(m, g);
+    pf2 Wg[4];
+    gather(Wgl, Wg, xb);
+    const float gPg = dot8(g, Wg);
     const float vis = v * is;
     const float vb = (a - v) * is;
     const float sb = (gPg - a * v) * is * is - 0.5f * (is - vis * vis);
     Rb += sb;
-    float gb[D];
-    float gsum = 0.f;
+    const float m2is = -2.f * is;
+    const pf2 vv = mk2(vis, vis), nn = mk2(m2is, m2is);
+    pf2 gb[4];
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-      gb[j] = fmaf(m[j], vis, fmaf(-2.f * is, Pg[j], (j == 0 || j == J) ? sb : 0.f));
-      if (j >= 1) gsum += gb[j];
-    }
+    for (int p = 0; p < 4; ++p) gb[p] = ffma2(m[p], vv, fmul2(Wg[p], nn));
+    el<0>(gb) += sb;
+    el<J>(gb) += sb;
     // W += sym(gb H^T), H = e_0 + e_J: columns 0 / J of every row, the whole rows 0 / J
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      const int row = sub + TPL * q;
+      const int row = sub * RPT + q;
       const bool hrow = (row == 0) || (row == J);
-      const float gbl = fmaf(ml[q], vis, fmaf(-2.f * is, Pgl[q], hrow ? sb : 0.f));
-      const float h = (row < D) ? 0.5f * gbl : 0.f;
+      const float gbl = fmaf(ml[q], vis, Wgl[q] * m2is) + (hrow ? sb : 0.f);   // == gb[row], same rounding
+      const float h = 0.5f * gbl;
       const float hs = hrow ? 0.5f : 0.f;
-      P[q][0] += h;
-      P[q][J] += h;
+      const pf2 hh = mk2(hs, hs);
+      float a8[8];
 #pragma unroll
-      for (int j = 0; j < D; ++j) P[q][j] = fmaf(hs, gb[j], P[q][j]);
-      rs[q] += h + ((row == J) ? 0.5f * gsum : 0.f);
+      for (int j = 0; j < 8; ++j) a8[j] = (j == 0 || j == J) ? h : 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        pf2 t = ffma2(hh, gb[p], P[q][p]);
+        if (2 * p == 0 || 2 * p == J || 2 * p + 1 == J) t = fadd2(t, mk2(a8[2 * p], a8[2 * p + 1]));
+        P[q][p] = t;
+      }
       ml[q] -= hrow ? vb : 0.f;
     }
-    m[0] -= vb;
-    m[J] -= vb;
+    el<0>(m) -= vb;
+    el<J>(m) -= vb;
     return vb;
-  }
-
-  template <int C>
-  __device__ __forceinline__ void disp_fwd(int c, float r, float* __restrict__ tp) {
-    if (C == S - 1 || c == C) fwd<C>(r, tp);
-    else disp_fwd<(C + 1 < S ? C + 1 : C)>(c, r, tp);
-  }
-  template <int C>
-  __device__ __forceinline__ float disp_bwd(int c, const float (&e)[8]) {
-    if (C == S - 1 || c == C) return bwd<C>(e);
-    else return disp_bwd<(C + 1 < S ? C + 1 : C)>(c, e);
   }
 };
 
+// compile-time loops over the season index (ascending / descending)
+template <int C, int N, class F>
+__device__ __forceinline__ void static_up(F&& f) {
+  if constexpr (C < N) {
+    f(std::integral_constant<int, C>{});
+    static_up<C + 1, N>(f);
+  }
+}
+template <int C, class F>
+__device__ __forceinline__ void static_down(F&& f) {
+  if constexpr (C >= 0) {
+    f(std::integral_constant<int, C>{});
+    static_down<C - 1>(f);
+  }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one bulk (TMA) copy global -> shared behind an mbarrier; called by ONE thread
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// one bulk (TMA) copy shared -> global as its own bulk group; called by ONE thread after the writers' proxy fence
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// register budget: each SM sub-partition owns 16 K registers, so 96 registers = 5 warps per sub-partition = 20 per SM
+// (10k lanes at TPL = 8 are 2500 warps = 17 per SM: one resident wave); 128 registers = 16 warps per SM at TPL = 4
 template <int S, int TPL>
-__global__ void __launch_bounds__(32)
+__global__ void __maxnreg__(TPL == 8 ? 96 : 128)
 k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
             float* logp, float* grad, float* __restrict__ tape, LeapArgs lf) {
   extern __shared__ __align__(16) float smem[];
   using Lane = CoopLane<S, TPL>;
-  constexpr int D = S + 1, LPW = 32 / TPL;
+  constexpr int LPW = 32 / TPL, KQM = 64 / TPL;
+  constexpr int RW = LPW * 8;                                    // floats per warp and step of the tape / an exchange row
+  constexpr int NRB = 3;                                         // tape ring: blocks of S steps (one season cycle)
   const int tid = threadIdx.x;
   const int sub = tid % TPL, lw = tid / TPL;
   const long B = (long)L.N * L.G;
@@ -230,29 +324,43 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   const int stride = (k + 1) * CI_TC;
   const int KQ = (k + TPL - 1) / TPL;
   const int nchunk = (T + CI_TC - 1) / CI_TC;
-  float* sb = smem + tid;                        // [KQ][32]: -beta / beta_bar of covariate sub + TPL q
-  float* sx = smem + KQ * 32;                    // staging buffer [smax][stride]
+  const int RS = coop_row_floats(T, LPW);
   const int smax = coop_series_max(L.G, LPW);
-  unsigned char* wbase = reinterpret_cast<unsigned char*>(sx + (long)smax * stride);
+  float* rbl = smem + lw * RS;                                  // residual / innovation / rbar row of this lane
+  float* xch = smem + LPW * RS;                                 // reverse-sweep exchange rows [2][RW]
+  float* ring = xch + 2 * RW;                                   // tape ring [NRB][S][RW]
+  float* sx = ring + NRB * S * RW;                              // design staging buffers [2][smax][stride]
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(sx + 2 * (long)smax * stride);
+  const uint32_t bar0 = smem_u32(wbase);                        // mbarriers: 2 design stages, NRB tape blocks
 
-  // ---- TMA staging of the warp's run of series (same protocol as ci_eval.cu, XM = 1) --------------------------
+  // ---- TMA staging of the warp's run of series: chunk tc -> stage tc & 1 ------------------------------------------
   const int n_lo = (int)(bw0 / L.G);
   const long b_last = (bw0 + LPW - 1 < B ? bw0 + LPW - 1 : B - 1);
   const int ns = (int)(b_last / L.G) - n_lo + 1;
-  XStaged xs;
-  xs.lane_x = sx + (long)(n - n_lo) * stride;
-  xs.bar = smem_u32(wbase);
-  xs.parity = 0u;
+  const float* lane_x = sx + (long)(n - n_lo) * stride;
+  const int stage_floats = smax * stride;
+  const float* xsrc = XY + (long)n_lo * stride;                 // chunk 0 of the warp's series run
+  const long xcs = (long)N * stride;                            // floats between consecutive chunks
+  const uint32_t xbytes = (uint32_t)ns * (uint32_t)stride * 4u;
+  const uint32_t sx_u32 = smem_u32(sx);
+  uint32_t xpar = 0u;                                           // bit s: parity to wait for on design stage s
+  auto x_issue = [&](int tc, int st) {                          // thread 0
+    bulk_load(sx_u32 + (uint32_t)(st * stage_floats) * 4u, xsrc + (long)tc * xcs, xbytes, bar0 + 8u * (uint32_t)st);
+  };
+  auto x_wait = [&](int st) {
+    mbar_wait(bar0 + 8u * (uint32_t)st, (xpar >> st) & 1u);
+    xpar ^= 1u << st;
+  };
   if (tid == 0) {
-    *reinterpret_cast<uint64_t*>(wbase + 16) = reinterpret_cast<uint64_t>(XY + (long)n_lo * stride);
-    *reinterpret_cast<uint32_t*>(wbase + 24) = (uint32_t)ns * (uint32_t)stride * 4u;
-    *reinterpret_cast<uint32_t*>(wbase + 28) = smem_u32(sx);
-    *reinterpret_cast<uint64_t*>(wbase + 32) = (uint64_t)((long)N * stride) * 4u;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs.bar) : "memory");
+#pragma unroll
+    for (int q = 0; q < 2 + NRB; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * q) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (tid == 0) xs.issue(0);
+  if (tid == 0) {
+    x_issue(0, 0);
+    if (nchunk > 1) x_issue(1, 1);
+  }
 
   // ---- u -> sigma^2's, -beta slices, prior + log-det (ci_params.cuh arithmetic, covariates split over sub-threads)
   const float* ub = u + b;
@@ -260,6 +368,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   const float sd = sc[SC_SD * N];
   const int Pn = num_params(k, S);
   float R, ql, qd, lp0;
+  float nbv[KQM];
   {
     const SoftplusPack p0 = softplus_pack(ub[0]), p1 = softplus_pack(ub[B]);
     const float so = sd * p0.sp, sl = sd * p1.sp;
@@ -269,23 +378,25 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     lps += -(2.f * CI_PRIOR_A + 1.f) * logf(so) - sc[SC_OBS_B * N] / R + p0.lsig;
     lps += -(2.f * CI_PRIOR_A + 1.f) * logf(sl) - sc[SC_LEVEL_B * N] / ql + p1.lsig;
     float lpp = 0.f;
+    float Gs = 0.f;
     if (k > 0) {
       const SoftplusPack pg = softplus_pack(ub[2 * B]), pn = softplus_pack(ub[3 * B]);
       const float gsv = pg.sp, gsn = pn.sp;
       lps += -1.5f * logf(gsv) - 0.5f / gsv - 0.5f * gsn * gsn + pg.lsig + pn.lsig;
-      const float Gs = -gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE;    // sb <- MINUS beta
-      for (int q = 0; q < KQ; ++q) {
-        const int j = sub + TPL * q;
-        float nb = 0.f;
-        if (j < k) {
-          const float a = ub[(long)(4 + j) * B], bb = ub[(long)(4 + k + j) * B], wn = ub[(long)(4 + 2 * k + j) * B];
-          const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(bb);
-          const float lsv = pa.sp, lsn = pb.sp;
-          lpp += -1.5f * logf(lsv) - 0.5f * rcp(lsv) - 0.5f * lsn * lsn - 0.5f * wn * wn + pa.lsig + pb.lsig;
-          nb = wn * lsn * sqrtf(lsv) * Gs;
-        }
-        sb[q * 32] = nb;
+      Gs = -gsn * sqrtf(gsv) * CI_WEIGHTS_PRIOR_SCALE;                // registers hold MINUS beta
+    }
+#pragma unroll
+    for (int q = 0; q < KQM; ++q) {
+      const int j = sub + TPL * q;
+      float nb = 0.f;
+      if (j < k) {
+        const float a = ub[(long)(4 + j) * B], bb = ub[(long)(4 + k + j) * B], wn = ub[(long)(4 + 2 * k + j) * B];
+        const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(bb);
+        const float lsv = pa.sp, lsn = pb.sp;
+        lpp += -1.5f * logf(lsv) - 0.5f * rcp(lsv) - 0.5f * lsn * lsn - 0.5f * wn * wn + pa.lsig + pb.lsig;
+        nb = wn * lsn * sqrtf(lsv) * Gs;
       }
+      nbv[q] = nb;
     }
     {
       const SoftplusPack pd = softplus_pack(ub[(long)(Pn - 1) * B]);
@@ -299,96 +410,180 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     lp0 = lps + group_sum<TPL>(lpp);
   }
 
+  // ---- pass 1: residuals of every step -> shared memory -------------------------------------------------------
+  for (int tc = 0; tc < nchunk; ++tc) {
+    const int st = tc & 1;
+    x_wait(st);
+    const float* __restrict__ xp = lane_x + st * stage_floats;
+    pf2 r01 = mk2(0.f, 0.f), r23 = mk2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < KQM; q += 2) {
+      if (q < KQ) {                                                   // pairs of covariates: half the uniform branches
+#pragma unroll
+        for (int qq = q; qq < q + 2; ++qq) {
+          const int j = sub + TPL * qq;
+          const float nb = nbv[qq];                                   // 0 past k
+          const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : 0) * CI_TC);
+          r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
+          r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
+        }
+      }
+    }
+    const float4 yv = *reinterpret_cast<const float4*>(xp + k * CI_TC);   // row k: centred series
+    // recursive halving over the TPL sub-threads: every sub-thread ends with one of the 4 step sums
+    float val;
+    int idx;
+    if constexpr (TPL == 8) {
+      const bool h4 = sub & 4, h2 = sub & 2;
+      pf2 keep = h4 ? r23 : r01;
+      const pf2 send = h4 ? r01 : r23;
+      keep.x += __shfl_xor_sync(0xffffffffu, send.x, 4, 8);
+      keep.y += __shfl_xor_sync(0xffffffffu, send.y, 4, 8);
+      val = h2 ? keep.y : keep.x;
+      val += __shfl_xor_sync(0xffffffffu, h2 ? keep.x : keep.y, 2, 8);
+      val += __shfl_xor_sync(0xffffffffu, val, 1, 8);
+      idx = (h4 ? 2 : 0) + (h2 ? 1 : 0);
+      val += h4 ? (h2 ? yv.w : yv.z) : (h2 ? yv.y : yv.x);
+    } else {
+      const bool h2 = sub & 2, h1 = sub & 1;
+      pf2 keep = h2 ? r23 : r01;
+      const pf2 send = h2 ? r01 : r23;
+      keep.x += __shfl_xor_sync(0xffffffffu, send.x, 2, 4);
+      keep.y += __shfl_xor_sync(0xffffffffu, send.y, 2, 4);
+      val = h1 ? keep.y : keep.x;
+      val += __shfl_xor_sync(0xffffffffu, h1 ? keep.x : keep.y, 1, 4);
+      idx = (h2 ? 2 : 0) + (h1 ? 1 : 0);
+      val += h2 ? (h1 ? yv.w : yv.z) : (h1 ? yv.y : yv.x);
+    }
+    rbl[tc * CI_TC + idx] = val;
+    __syncwarp();                                                     // the staged chunk is consumed
+    if (tid == 0 && tc + 2 < nchunk) x_issue(tc + 2, st);
+  }
+  // the stage buffers are free: chunks 0 / 1 of the beta_bar pass stream in behind the filter sweeps
+  if (tid == 0 && k > 0) {
+    x_issue(0, nchunk & 1);
+    if (nchunk > 1) x_issue(1, (nchunk + 1) & 1);
+  }
+
   Lane ln(sub, R, ql, qd);
   ln.init_forward(sc[SC_M0 * N], sc[SC_P0 * N]);
-  const int tstep = (int)gridDim.x * LPW * 8;                       // floats between consecutive steps
-  float* tp = tape + ((long)blockIdx.x * LPW + lw) * 8;
+  // tape [warps][T][RW]: a warp's entries of consecutive steps are contiguous, S steps = one bulk copy
+  float* wtape = tape + (long)blockIdx.x * T * RW;
+  const int nblk = (T + S - 1) / S;
+  const uint32_t ring_u32 = smem_u32(ring);
 
-  // ---- forward sweep ----------------------------------------------------------------------------------------
+  // ---- pass 2: forward filter, one season cycle per block, gains -> tape ring -> bulk store ----------------------
   {
-    int c = 0;
-    for (int tc = 0; tc < nchunk; ++tc) {
-      xs.acquire();
-      const float* __restrict__ xp = xs.lane_x;
-      pf2 r01 = mk2(0.f, 0.f), r23 = mk2(0.f, 0.f);
-      for (int q = 0; q < KQ; ++q) {
-        const int j = sub + TPL * q;
-        const float nb = sb[q * 32];                                // 0 past k
-        const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : k) * CI_TC);
-        r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
-        r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
+    auto fwd_block = [&](int blk, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const int t0 = blk * S;
+      const int nrow = FULL ? S : T - t0;
+      const int rbuf = blk & 1;
+      if (blk >= 2) {                                                 // the store of block blk - 2 has read its rows
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
       }
-      const float4 yv = *reinterpret_cast<const float4*>(xp + k * CI_TC);   // row k: centred series
-      xs.release(tc + 1 < nchunk ? tc + 1 : -1);
-      float rr[CI_TC] = {r01.x, r01.y, r23.x, r23.y};
+      float* rows = ring + rbuf * (S * RW) + lw * 8;
+      float rr[S];
 #pragma unroll
-      for (int i = 0; i < CI_TC; ++i) rr[i] = group_sum<TPL>(rr[i]);
-      rr[0] += yv.x; rr[1] += yv.y; rr[2] += yv.z; rr[3] += yv.w;
-      const int nstep = (T - tc * CI_TC) < CI_TC ? (T - tc * CI_TC) : CI_TC;
-      for (int i = 0; i < nstep; ++i) {
-        const float r = (i == 0) ? rr[0] : (i == 1) ? rr[1] : (i == 2) ? rr[2] : rr[3];
-        ln.template disp_fwd<0>(c, r, tp);
-        tp += tstep;
-        c = (c + 1 == S) ? 0 : c + 1;
-      }
-    }
+      for (int c = 0; c < S; ++c) rr[c] = (FULL || c < nrow) ? rbl[t0 + c] : 0.f;
+      static_up<0, S>([&](auto cc) {
+        constexpr int C = decltype(cc)::value;
+        if (FULL || C < nrow) {
+          const float vout = ln.template fwd<C>(rr[C], rows + C * RW);
+          if (sub == 0) rbl[t0 + C] = vout;
+        }
+      });
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // ring rows -> visible to the bulk store
+      __syncwarp();
+      if (tid == 0)
+        bulk_store(wtape + (long)t0 * RW, ring_u32 + (uint32_t)(rbuf * S * RW) * 4u, (uint32_t)(nrow * RW) * 4u);
+    };
+    const int nfull = T / S;
+    for (int blk = 0; blk < nfull; ++blk) fwd_block(blk, std::true_type{});
+    if (nfull < nblk) fwd_block(nfull, std::false_type{});
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // tape complete before it is re-read
+    __syncwarp();
   }
   const float ll = -0.5f * (fmaf(ln.acc, 0.6931471805599453f, ln.quad) + (float)(T - ln.nmask) * CI_LOG_2PI);
+  if (sub == 0)
+    for (int t = T; t < nchunk * CI_TC; ++t) rbl[t] = 0.f;            // steps past T carry no adjoint
 
-  // ---- reverse sweep ----------------------------------------------------------------------------------------
-  for (int q = 0; q < KQ; ++q) sb[q * 32] = 0.f;
+  // ---- pass 3: reverse sweep, tape blocks stream back NRB cycles ahead ---------------------------------------
   ln.init_reverse();
   {
-    tp -= tstep;                                                    // entry of step T - 1
-    float cur[8], nxt[8];
-    {
-      const float4 a = *reinterpret_cast<const float4*>(tp), bq = *reinterpret_cast<const float4*>(tp + 4);
-      cur[0] = a.x; cur[1] = a.y; cur[2] = a.z; cur[3] = a.w;
-      cur[4] = bq.x; cur[5] = bq.y; cur[6] = bq.z; cur[7] = bq.w;
-    }
-    float rb0 = 0.f, rb1 = 0.f, rb2 = 0.f, rb3 = 0.f;
-    int c = (T - 1) % S;
-    for (int t = T - 1; t >= 0; --t) {
-      const int i = t & (CI_TC - 1);
-      if (t > 0) {
-        const float* tq = tp - tstep;
-        const float4 a = *reinterpret_cast<const float4*>(tq), bq = *reinterpret_cast<const float4*>(tq + 4);
-        nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w;
-        nxt[4] = bq.x; nxt[5] = bq.y; nxt[6] = bq.z; nxt[7] = bq.w;
-        if (sub == 0 && t > CI_TAPE_AHEAD) prefetch_l2(tp - (long)CI_TAPE_AHEAD * tstep);
-      }
-      const float rb = ln.template disp_bwd<0>(c, cur);
-      rb0 = (i == 0) ? rb : rb0;
-      rb1 = (i == 1) ? rb : rb1;
-      rb2 = (i == 2) ? rb : rb2;
-      rb3 = (i == 3) ? rb : rb3;
-      if (i == 0) {
-        const int tc = t / CI_TC;
-        if (tc != nchunk - 1) xs.acquire();                         // the last forward chunk is still resident
-        if (k > 0) {
-          const pf2 n01 = mk2(-rb0, -rb1), n23 = mk2(-rb2, -rb3);
-          const float* __restrict__ xp = xs.lane_x;
-          for (int q = 0; q < KQ; ++q) {
-            const int j = sub + TPL * q;
-            const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : k) * CI_TC);
-            pf2 a = mk2(sb[q * 32], 0.f);
-            a = ffma2(mk2(x.x, x.y), n01, a);
-            a = ffma2(mk2(x.z, x.w), n23, a);
-            sb[q * 32] = a.x + a.y;
-          }
-        }
-        xs.release(tc - 1);
-        rb0 = rb1 = rb2 = rb3 = 0.f;
-      }
-      tp -= tstep;
-      c = (c == 0) ? S - 1 : c - 1;
+    uint32_t tpar = 0u;                                               // bit q: parity to wait for on ring buffer q
+    auto t_issue = [&](int blk, int q) {                              // thread 0
+      const int t0 = blk * S;
+      const int nrow = (T - t0) < S ? (T - t0) : S;
+      bulk_load(ring_u32 + (uint32_t)(q * S * RW) * 4u, wtape + (long)t0 * RW, (uint32_t)(nrow * RW) * 4u,
+                bar0 + 8u * (uint32_t)(2 + q));
+    };
+    if (tid == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+      for (int q = 0; q < NRB; ++q)
+        if (nblk - 1 - q >= 0) t_issue(nblk - 1 - q, q);
     }
+    int q = 0;
+    auto bwd_block = [&](int blk, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const int t0 = blk * S;
+      const int nrow = FULL ? S : T - t0;
+      mbar_wait(bar0 + 8u * (uint32_t)(2 + q), (tpar >> q) & 1u);
+      tpar ^= 1u << q;
+      const float* rows = ring + q * (S * RW) + lw * 8;
+      float vr[S];
+#pragma unroll
+      for (int c = 0; c < S; ++c) vr[c] = (FULL || c < nrow) ? rbl[t0 + c] : 0.f;
+      static_down<S - 1>([&](auto cc) {
+        constexpr int C = decltype(cc)::value;
+        if (FULL || C < nrow) {
+          const float4 ea = *reinterpret_cast<const float4*>(rows + C * RW);
+          const float4 eb = *reinterpret_cast<const float4*>(rows + C * RW + 4);
+          const float vb = ln.template bwd<C>(ea, eb, vr[C], xch + (C & 1) * RW + lw * 8);
+          if (sub == 0) rbl[t0 + C] = vb;
+        }
+      });
+      __syncwarp();                                                   // ring buffer q and both exchange rows are free
+      if (tid == 0 && blk - NRB >= 0) t_issue(blk - NRB, q);
+      q = (q == NRB - 1) ? 0 : q + 1;
+    };
+    int blk = nblk - 1;
+    if (T % S != 0) bwd_block(blk--, std::false_type{});
+    for (; blk >= 0; --blk) bwd_block(blk, std::true_type{});
   }
   const float Rb = ln.Rb;
-  const float qlb = __shfl_sync(0xffffffffu, ln.qlacc, 0, TPL);     // row 0 lives in sub-thread 0
+  const float qlb = __shfl_sync(0xffffffffu, ln.qlacc, 0, TPL);       // row 0 lives in sub-thread 0
   const float qdb = group_sum<TPL>(ln.qdacc);
+  __syncwarp();                                                       // rbar rows complete
+
+  // ---- pass 4: beta_bar_j = -sum_t rbar_t X_tj ---------------------------------------------------------------------
+  pf2 bacc[KQM];
+#pragma unroll
+  for (int q = 0; q < KQM; ++q) bacc[q] = mk2(0.f, 0.f);
+  if (k > 0) {
+    for (int tc = 0; tc < nchunk; ++tc) {
+      const int st = (nchunk + tc) & 1;
+      x_wait(st);
+      const float* __restrict__ xp = lane_x + st * stage_floats;
+      const float4 rb = *reinterpret_cast<const float4*>(rbl + tc * CI_TC);
+      const pf2 n01 = mk2(rb.x, rb.y), n23 = mk2(rb.z, rb.w);
+#pragma unroll
+      for (int q = 0; q < KQM; q += 2) {
+        if (q < KQ) {
+#pragma unroll
+          for (int qq = q; qq < q + 2; ++qq) {
+            const int j = sub + TPL * qq;
+            const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : 0) * CI_TC);
+            bacc[qq] = ffma2(mk2(x.x, x.y), n01, bacc[qq]);
+            bacc[qq] = ffma2(mk2(x.z, x.w), n23, bacc[qq]);
+          }
+        }
+      }
+      __syncwarp();
+      if (tid == 0 && tc + 2 < nchunk) x_issue(tc + 2, st);
+    }
+  }
 
   // ---- VJP through the parameter transforms + priors; leapfrog kick / drift on the fresh component -----------
   // every scalar of u that more than one sub-thread reads is read BEFORE any sub-thread may drift it
@@ -420,11 +615,12 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     gsn = pn.sp;
     sq_gsv = sqrtf(gsv);
     const float Gs = gsn * sq_gsv * CI_WEIGHTS_PRIOR_SCALE;
-    for (int q = 0; q < KQ; ++q) {
+#pragma unroll
+    for (int q = 0; q < KQM; ++q) {
       const int j = sub + TPL * q;
       if (j < k) {
         const float a = ub[(long)(4 + j) * B], bq = ub[(long)(4 + k + j) * B], wn = ub[(long)(4 + 2 * k + j) * B];
-        const float bb = sb[q * 32];
+        const float bb = -(bacc[q].x + bacc[q].y);
         const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(bq);
         const float lsv = pa.sp, lsn = pb.sp;
         const float sq = sqrtf(lsv);
@@ -468,25 +664,37 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-static int g_coop_tpl = 8;              // sub-threads per lane (8, 4, 2); 0 disables the cooperative kernel
-static long g_coop_max_lanes = -1;      // -1 = one resident wave of the chosen TPL
+static int g_coop_tpl = -1;             // sub-threads per lane: 8, 4; 0 disables the cooperative kernel; -1 = by lane count
+static long g_coop_max_lanes = -1;      // -1 = default crossover to the thread-per-lane kernel
 
 void coop_set_option(int tpl, long max_lanes) {
   g_coop_tpl = tpl;
   g_coop_max_lanes = max_lanes;
 }
 
+static int coop_pick_tpl(long B) {
+  if (g_coop_tpl >= 0) return g_coop_tpl;
+  return B <= CI_COOP_TPL8_LANES ? 8 : 4;
+}
+
+static size_t coop_smem_bytes(const ci_layout* L, int tpl) {
+  const int lpw = 32 / tpl;
+  return ((size_t)lpw * coop_row_floats(L->T, lpw) + 2 * lpw * 8 + 3 * (size_t)L->S * lpw * 8 +
+          2 * (size_t)coop_series_max(L->G, lpw) * (L->k + 1) * CI_TC) * 4 + 64;
+}
+
 bool coop_eligible(const ci_layout* L) {
   if (g_coop_tpl == 0) return false;
-  if (!ci_reg_path(L) || L->r != 1 || L->S < 2 || L->S > CI_MAX_EFF_S) return false;
+  if (!ci_reg_path(L) || L->r != 1 || L->S < 2 || L->S > CI_MAX_EFF_S || L->k > 64) return false;
   const long B = (long)L->N * L->G;
-  const long lim = g_coop_max_lanes >= 0 ? g_coop_max_lanes : (long)148 * 32 * (32 / g_coop_tpl);
-  return B <= lim;
+  const long lim = g_coop_max_lanes >= 0 ? g_coop_max_lanes : CI_COOP_MAX_LANES;
+  if (B > lim) return false;
+  return coop_smem_bytes(L, coop_pick_tpl(B)) <= 96 * 1024;
 }
 
 size_t coop_tape_floats(const ci_layout* L) {
-  // any TPL: lanes padded to a whole warp of the widest lane count (16 lanes at TPL = 2)
-  const size_t Bp = ((size_t)L->N * L->G + 15) / 16 * 16;
+  // [warps][T][lanes per warp * 8]: lanes padded to a whole warp of the widest lane count (8 lanes at TPL = 4)
+  const size_t Bp = ((size_t)L->N * L->G + 7) / 8 * 8;
   return (size_t)L->T * Bp * 8;
 }
 
@@ -495,35 +703,38 @@ static int launch_coop_t(const ci_layout* L, const ci_data* D, const float* d_u,
                          float* tape, cudaStream_t st, const LeapArgs& lf) {
   constexpr int LPW = 32 / TPL;
   const long B = (long)L->N * L->G;
-  const int KQ = (L->k + TPL - 1) / TPL;
-  const size_t smem = (size_t)KQ * 32 * 4 + (size_t)coop_series_max(L->G, LPW) * (L->k + 1) * CI_TC * 4 + 48;
+  const size_t smem = coop_smem_bytes(L, TPL);
   auto kern = k_eval_coop<S, TPL>;
-  if (smem > 48 * 1024) {
-    if (smem > 227 * 1024) return fail(CI_ERR_UNSUPPORTED, "k=%d covariates exceed the shared-memory budget", L->k);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
   }
   kern<<<(unsigned)((B + LPW - 1) / LPW), 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, lf);
   return CI_OK;
 }
 
+template <int TPL>
+static int launch_coop_s(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
+                         float* tape, cudaStream_t st, const LeapArgs& lf) {
+  switch (L->S) {
+    case 2: return launch_coop_t<2, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    case 3: return launch_coop_t<3, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    case 4: return launch_coop_t<4, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    case 5: return launch_coop_t<5, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    case 6: return launch_coop_t<6, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    case 7: return launch_coop_t<7, TPL>(L, D, d_u, d_logp, d_grad, tape, st, lf);
+    default: return fail(CI_ERR_UNSUPPORTED, "cooperative evaluation needs 2 <= nseasons <= 7");
+  }
+}
+
 int launch_eval_coop(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                      float* tape, cudaStream_t st, const LeapArgs& lf) {
-  int rc = CI_OK;
-#define CI_COOP_S(TPL_)                                                                              \
-  switch (L->S) {                                                                                    \
-    case 2: rc = launch_coop_t<2, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    case 3: rc = launch_coop_t<3, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    case 4: rc = launch_coop_t<4, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    case 5: rc = launch_coop_t<5, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    case 6: rc = launch_coop_t<6, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    case 7: rc = launch_coop_t<7, TPL_>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;             \
-    default: return fail(CI_ERR_UNSUPPORTED, "cooperative evaluation needs 2 <= nseasons <= 7");     \
-  }
-  if (g_coop_tpl == 8) CI_COOP_S(8)
-  else if (g_coop_tpl == 4) CI_COOP_S(4)
-  else CI_COOP_S(2)
-#undef CI_COOP_S
+  const int tpl = coop_pick_tpl((long)L->N * L->G);
+  const int rc = tpl == 8 ? launch_coop_s<8>(L, D, d_u, d_logp, d_grad, tape, st, lf)
+                          : launch_coop_s<4>(L, D, d_u, d_logp, d_grad, tape, st, lf);
   if (rc) return rc;
   CI_CHECK_LAUNCH();
   return CI_OK;
