@@ -36,13 +36,19 @@
 #include "ci_kalman_eff.cuh"
 
 // lane counts served by the cooperative kernel (measured crossovers, scripts/ab_coop.py; B200, k = 50, S = 7)
-#define CI_COOP_TPL8_LANES 12000L   // up to here 8 sub-threads per lane, above 4
-#define CI_COOP_MAX_LANES 24000L    // above: thread-per-lane kernel
+// eval ms at lanes =      1000   5000   10000  11800  15000  20000     (gpurun_out/ab_coop7_k50.jsonl)
+//   thread per lane       0.446  0.468  0.499  0.505  0.502  0.521
+//   8 sub-threads         0.132  0.216  0.324  0.394  0.460  0.585
+//   4 sub-threads         0.179  0.225  0.295  0.297  0.476  0.512
+#define CI_COOP_TPL8_LANES 7500L    // up to here 8 sub-threads per lane, above 4
+#define CI_COOP_MAX_LANES 13000L    // one resident wave at 4 sub-threads; above: thread-per-lane kernel
+#define CI_COOP_MAX_STAGES 8        // design-matrix chunks in flight per warp (TMA stages)
 
 namespace ci {
 
 // lanes a warp of the cooperative kernel can touch -> series it can touch (lanes of a series are contiguous)
 __host__ __device__ inline int coop_series_max(int G, int lpw) {
+  if (G % lpw == 0) return 1;                  // a warp's lanes never straddle a series
   const int a = (lpw + G - 2) / G + 1;
   return a < lpw ? a : lpw;
 }
@@ -288,13 +294,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-// one bulk (TMA) copy global -> shared behind an mbarrier; called by ONE thread
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// bulk (TMA) copies global -> shared behind an mbarrier; called by ONE thread after a warp barrier.  The buffer being
+// overwritten was last READ through the generic proxy by threads that have passed that barrier, which orders the
+// reuse (the consumer-release / producer-acquire pattern of TMA pipelines; no cross-proxy fence on this direction).
+__device__ __forceinline__ void bulk_expect(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_in(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  bulk_expect(bar, bytes);
+  bulk_copy_in(dst, src, bytes, bar);
 }
 // one bulk (TMA) copy shared -> global as its own bulk group; called by ONE thread after the writers' proxy fence
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
@@ -307,7 +320,7 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
 template <int S, int TPL>
 __global__ void __maxnreg__(TPL == 8 ? 96 : 128)
 k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
-            float* logp, float* grad, float* __restrict__ tape, LeapArgs lf) {
+            float* logp, float* grad, float* __restrict__ tape, LeapArgs lf, int nst) {
   extern __shared__ __align__(16) float smem[];
   using Lane = CoopLane<S, TPL>;
   constexpr int LPW = 32 / TPL, KQM = 64 / TPL;
@@ -326,30 +339,41 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   const int nchunk = (T + CI_TC - 1) / CI_TC;
   const int RS = coop_row_floats(T, LPW);
   const int smax = coop_series_max(L.G, LPW);
+  // shared memory: residual rows | region U | mbarriers.  U holds the nst design-matrix stages during passes 1 and 4
+  // and the exchange rows + tape ring during passes 2 and 3 (the passes never overlap).
   float* rbl = smem + lw * RS;                                  // residual / innovation / rbar row of this lane
-  float* xch = smem + LPW * RS;                                 // reverse-sweep exchange rows [2][RW]
+  float* sx = smem + LPW * RS;                                  // design staging buffers [nst][smax][stride]
+  float* xch = sx;                                              // reverse-sweep exchange rows [2][RW]
   float* ring = xch + 2 * RW;                                   // tape ring [NRB][S][RW]
-  float* sx = ring + NRB * S * RW;                              // design staging buffers [2][smax][stride]
-  unsigned char* wbase = reinterpret_cast<unsigned char*>(sx + 2 * (long)smax * stride);
-  const uint32_t bar0 = smem_u32(wbase);                        // mbarriers: 2 design stages, NRB tape blocks
+  const int stage_floats = smax * stride;
+  const int ufl = max(nst * stage_floats, (2 + NRB * S) * RW);
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(sx + (ufl + 3) / 4 * 4);
+  const uint32_t bar0 = smem_u32(wbase);                        // mbarriers: 2 design-stage halves, NRB tape blocks
 
   // ---- TMA staging of the warp's run of series: chunk tc -> stage tc & 1 ------------------------------------------
   const int n_lo = (int)(bw0 / L.G);
   const long b_last = (bw0 + LPW - 1 < B ? bw0 + LPW - 1 : B - 1);
   const int ns = (int)(b_last / L.G) - n_lo + 1;
   const float* lane_x = sx + (long)(n - n_lo) * stride;
-  const int stage_floats = smax * stride;
   const float* xsrc = XY + (long)n_lo * stride;                 // chunk 0 of the warp's series run
   const long xcs = (long)N * stride;                            // floats between consecutive chunks
   const uint32_t xbytes = (uint32_t)ns * (uint32_t)stride * 4u;
   const uint32_t sx_u32 = smem_u32(sx);
-  uint32_t xpar = 0u;                                           // bit s: parity to wait for on design stage s
-  auto x_issue = [&](int tc, int st) {                          // thread 0
-    bulk_load(sx_u32 + (uint32_t)(st * stage_floats) * 4u, xsrc + (long)tc * xcs, xbytes, bar0 + 8u * (uint32_t)st);
+  // the nst = 2 h stages form two halves of h chunks; one mbarrier and one issue block per half
+  const int xh = nst >> 1;
+  const int nhalf = (nchunk + xh - 1) / xh;
+  uint32_t xpar = 0u;                                           // bit p: parity to wait for on half p
+  auto x_issue_half = [&](int hb, int p) {                      // thread 0
+    const int tc0 = hb * xh;
+    const int cnt = (nchunk - tc0) < xh ? (nchunk - tc0) : xh;
+    const uint32_t bar = bar0 + 8u * (uint32_t)p;
+    bulk_expect(bar, xbytes * (uint32_t)cnt);
+    for (int i = 0; i < cnt; ++i)
+      bulk_copy_in(sx_u32 + (uint32_t)((p * xh + i) * stage_floats) * 4u, xsrc + (long)(tc0 + i) * xcs, xbytes, bar);
   };
-  auto x_wait = [&](int st) {
-    mbar_wait(bar0 + 8u * (uint32_t)st, (xpar >> st) & 1u);
-    xpar ^= 1u << st;
+  auto x_wait_half = [&](int p) {
+    mbar_wait(bar0 + 8u * (uint32_t)p, (xpar >> p) & 1u);
+    xpar ^= 1u << p;
   };
   if (tid == 0) {
 #pragma unroll
@@ -358,9 +382,13 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   }
   __syncwarp();
   if (tid == 0) {
-    x_issue(0, 0);
-    if (nchunk > 1) x_issue(1, 1);
+    x_issue_half(0, 0);
+    if (nhalf > 1) x_issue_half(1, 1);
   }
+  // shared-memory offsets of this sub-thread's covariate rows inside a staged chunk (rows past k alias row 0)
+  int xoff[KQM];
+#pragma unroll
+  for (int q = 0; q < KQM; ++q) xoff[q] = ((sub + TPL * q) < k ? (sub + TPL * q) : 0) * CI_TC;
 
   // ---- u -> sigma^2's, -beta slices, prior + log-det (ci_params.cuh arithmetic, covariates split over sub-threads)
   const float* ub = u + b;
@@ -411,24 +439,27 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   }
 
   // ---- pass 1: residuals of every step -> shared memory -------------------------------------------------------
-  for (int tc = 0; tc < nchunk; ++tc) {
-    const int st = tc & 1;
-    x_wait(st);
-    const float* __restrict__ xp = lane_x + st * stage_floats;
-    pf2 r01 = mk2(0.f, 0.f), r23 = mk2(0.f, 0.f);
+  for (int hb = 0; hb < nhalf; ++hb) {
+   const int hp = hb & 1;
+   x_wait_half(hp);
+   const int tce = (hb + 1) * xh < nchunk ? (hb + 1) * xh : nchunk;
+   for (int tc = hb * xh; tc < tce; ++tc) {
+    const float* __restrict__ xp = lane_x + (hp * xh + (tc - hb * xh)) * stage_floats;
+    pf2 r01 = mk2(0.f, 0.f), r23 = mk2(0.f, 0.f), s01 = mk2(0.f, 0.f), s23 = mk2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < KQM; q += 2) {
       if (q < KQ) {                                                   // pairs of covariates: half the uniform branches
-#pragma unroll
-        for (int qq = q; qq < q + 2; ++qq) {
-          const int j = sub + TPL * qq;
-          const float nb = nbv[qq];                                   // 0 past k
-          const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : 0) * CI_TC);
-          r01 = ffma2(mk2(nb, nb), mk2(x.x, x.y), r01);
-          r23 = ffma2(mk2(nb, nb), mk2(x.z, x.w), r23);
-        }
+        const float4 x0 = *reinterpret_cast<const float4*>(xp + xoff[q]);
+        const float4 x1 = *reinterpret_cast<const float4*>(xp + xoff[q + 1]);
+        const float n0 = nbv[q], n1 = nbv[q + 1];                     // 0 past k
+        r01 = ffma2(mk2(n0, n0), mk2(x0.x, x0.y), r01);
+        r23 = ffma2(mk2(n0, n0), mk2(x0.z, x0.w), r23);
+        s01 = ffma2(mk2(n1, n1), mk2(x1.x, x1.y), s01);
+        s23 = ffma2(mk2(n1, n1), mk2(x1.z, x1.w), s23);
       }
     }
+    r01 = fadd2(r01, s01);
+    r23 = fadd2(r23, s23);
     const float4 yv = *reinterpret_cast<const float4*>(xp + k * CI_TC);   // row k: centred series
     // recursive halving over the TPL sub-threads: every sub-thread ends with one of the 4 step sums
     float val;
@@ -456,13 +487,9 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
       val += h2 ? (h1 ? yv.w : yv.z) : (h1 ? yv.y : yv.x);
     }
     rbl[tc * CI_TC + idx] = val;
-    __syncwarp();                                                     // the staged chunk is consumed
-    if (tid == 0 && tc + 2 < nchunk) x_issue(tc + 2, st);
-  }
-  // the stage buffers are free: chunks 0 / 1 of the beta_bar pass stream in behind the filter sweeps
-  if (tid == 0 && k > 0) {
-    x_issue(0, nchunk & 1);
-    if (nchunk > 1) x_issue(1, (nchunk + 1) & 1);
+   }
+   __syncwarp();                                                      // the staged half is consumed
+   if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
   }
 
   Lane ln(sub, R, ql, qd);
@@ -562,26 +589,32 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
 #pragma unroll
   for (int q = 0; q < KQM; ++q) bacc[q] = mk2(0.f, 0.f);
   if (k > 0) {
-    for (int tc = 0; tc < nchunk; ++tc) {
-      const int st = (nchunk + tc) & 1;
-      x_wait(st);
-      const float* __restrict__ xp = lane_x + st * stage_floats;
-      const float4 rb = *reinterpret_cast<const float4*>(rbl + tc * CI_TC);
-      const pf2 n01 = mk2(rb.x, rb.y), n23 = mk2(rb.z, rb.w);
+    if (tid == 0) {
+      x_issue_half(0, 0);
+      if (nhalf > 1) x_issue_half(1, 1);
+    }
+    for (int hb = 0; hb < nhalf; ++hb) {
+      const int hp = hb & 1;
+      x_wait_half(hp);
+      const int tce = (hb + 1) * xh < nchunk ? (hb + 1) * xh : nchunk;
+      for (int tc = hb * xh; tc < tce; ++tc) {
+        const float* __restrict__ xp = lane_x + (hp * xh + (tc - hb * xh)) * stage_floats;
+        const float4 rb = *reinterpret_cast<const float4*>(rbl + tc * CI_TC);
+        const pf2 n01 = mk2(rb.x, rb.y), n23 = mk2(rb.z, rb.w);
 #pragma unroll
-      for (int q = 0; q < KQM; q += 2) {
-        if (q < KQ) {
-#pragma unroll
-          for (int qq = q; qq < q + 2; ++qq) {
-            const int j = sub + TPL * qq;
-            const float4 x = *reinterpret_cast<const float4*>(xp + (j < k ? j : 0) * CI_TC);
-            bacc[qq] = ffma2(mk2(x.x, x.y), n01, bacc[qq]);
-            bacc[qq] = ffma2(mk2(x.z, x.w), n23, bacc[qq]);
+        for (int q = 0; q < KQM; q += 2) {
+          if (q < KQ) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xp + xoff[q]);
+            const float4 x1 = *reinterpret_cast<const float4*>(xp + xoff[q + 1]);
+            bacc[q] = ffma2(mk2(x0.x, x0.y), n01, bacc[q]);
+            bacc[q + 1] = ffma2(mk2(x1.x, x1.y), n01, bacc[q + 1]);
+            bacc[q] = ffma2(mk2(x0.z, x0.w), n23, bacc[q]);
+            bacc[q + 1] = ffma2(mk2(x1.z, x1.w), n23, bacc[q + 1]);
           }
         }
       }
       __syncwarp();
-      if (tid == 0 && tc + 2 < nchunk) x_issue(tc + 2, st);
+      if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
     }
   }
 
@@ -677,10 +710,21 @@ static int coop_pick_tpl(long B) {
   return B <= CI_COOP_TPL8_LANES ? 8 : 4;
 }
 
+// design-matrix stages that fit beside the residual rows when the SM holds `warps` CTAs (at least 2, at most 8)
+static int coop_stages(const ci_layout* L, int tpl) {
+  const int lpw = 32 / tpl, warps = tpl == 8 ? 17 : 16;
+  const long budget = (227L * 1024 - warps * 1024) / warps - (long)lpw * coop_row_floats(L->T, lpw) * 4 - 128;
+  const long stage = (long)coop_series_max(L->G, lpw) * (L->k + 1) * CI_TC * 4;
+  const long ring = (2 + 3 * (long)L->S) * lpw * 8 * 4;           // the stages alias the tape ring: that much is free
+  long nst = (budget > ring ? budget : ring) / stage;
+  nst = nst < 2 ? 2 : (nst > CI_COOP_MAX_STAGES ? CI_COOP_MAX_STAGES : nst);
+  return (int)(nst & ~1L);                                          // two halves of nst / 2 chunks
+}
 static size_t coop_smem_bytes(const ci_layout* L, int tpl) {
   const int lpw = 32 / tpl;
-  return ((size_t)lpw * coop_row_floats(L->T, lpw) + 2 * lpw * 8 + 3 * (size_t)L->S * lpw * 8 +
-          2 * (size_t)coop_series_max(L->G, lpw) * (L->k + 1) * CI_TC) * 4 + 64;
+  const size_t stages = (size_t)coop_stages(L, tpl) * coop_series_max(L->G, lpw) * (L->k + 1) * CI_TC;
+  const size_t ring = (2 + 3 * (size_t)L->S) * lpw * 8;
+  return ((size_t)lpw * coop_row_floats(L->T, lpw) + (stages > ring ? stages : ring) + 4) * 4 + 8 * (CI_COOP_MAX_STAGES + 3) + 16;
 }
 
 bool coop_eligible(const ci_layout* L) {
@@ -712,7 +756,8 @@ static int launch_coop_t(const ci_layout* L, const ci_data* D, const float* d_u,
     if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<(unsigned)((B + LPW - 1) / LPW), 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, lf);
+  kern<<<(unsigned)((B + LPW - 1) / LPW), 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, lf,
+                                                          coop_stages(L, TPL));
   return CI_OK;
 }
 
