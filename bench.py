@@ -8,7 +8,11 @@ log-prob + adjoint-gradient evaluation) over a batch of independent series.
 Metric (BASELINE.json): HMC posterior draws/sec (whole job, all ranks); the Kalman log-prob+grad
 evaluation rate and its roofline are reported in the same JSON line.  Workload = BASELINE.json
 configs[3]: 10k series x 365 steps, weekly seasonality, SparseLinearRegression with 50 covariates,
-8 chains per series; weak scaling (every rank owns `--series` series, no data-path collective).
+8 chains per series.  Headline = weak scaling (every rank owns `--series` series, no data-path collective);
+the same JSON line carries a `strong` record -- the NAMED split of configs[3]: `--series` series in TOTAL sharded over
+the ranks (`distributed.shard_range`), the [N,21] summary rows gathered over NCCL inside the timed region -- plus a
+`full_fit` record (VI initialisation + warm-up + draws + filter + forecast + summary through `causal_impact_batch`),
+the configs[4] evaluation and the box's host-to-device copy ceiling.
 A "step" is one HMC transition of every chain = N*C posterior draws = N*C*15 evaluations.
 """
 import argparse
@@ -48,7 +52,11 @@ def parse_args():
     ap.add_argument('--init-vi-steps', type=int, default=150, help='untimed VI initialisation (fit_with_hmc: 150)')
     ap.add_argument('--init-vi-samples', type=int, default=5, help='fit_with_hmc: 5')
     ap.add_argument('--init-warmup', type=int, default=50, help='untimed adaptive warm-up transitions (fit_with_hmc: 50)')
-    ap.add_argument('--cpu-sample-series', type=int, default=0, help='0 = calibrate to a few seconds per step')
+    ap.add_argument('--cpu-sample-series', type=int, default=128, help='series of the bounded CPU sample (both CPU legs)')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling / full-fit records')
+    ap.add_argument('--no-extra', action='store_true', help='skip the configs[4] evaluation and copy-ceiling records')
+    ap.add_argument('--fit-results', type=int, default=100, help='full_fit: kept draws per chain (fit_with_hmc: 100)')
+    ap.add_argument('--fit-warmup', type=int, default=50, help='full_fit: warm-up transitions (fit_with_hmc: 50)')
     return ap.parse_args()
 
 
@@ -56,7 +64,7 @@ def parse_args():
 # synthetic workload: level random walk + seasonal + sparse regression + noise,
 # standardised by the pre-period mean / std as the library does by default
 # ------------------------------------------------------------------------------------------------
-def synth(N, T, Tf, k, S, seed, device):
+def synth(N, T, Tf, k, S, seed, device, full=False):
     g = torch.Generator(device=device).manual_seed(seed)
     Tt = T + Tf
     X = torch.randn(N, Tt, max(k, 1), generator=g, device=device)[:, :, :k]
@@ -77,6 +85,8 @@ def synth(N, T, Tf, k, S, seed, device):
     mu = y[:, :T].mean(dim=1, keepdim=True)
     sd = y[:, :T].std(dim=1, unbiased=False, keepdim=True)
     y = (y - mu) / sd
+    if full:                                  # + the injected post-period effect in standardised units
+        return y[:, :T].contiguous(), y[:, T:].contiguous(), X.contiguous(), (0.5 / sd).reshape(-1)
     return y[:, :T].contiguous(), X.contiguous()
 
 
@@ -158,16 +168,45 @@ def cpu_step_time(args, ns, nsteps=1, seed=1):
     return (time.perf_counter() - t0) / nsteps
 
 
-def cpu_calibrate(args):
-    if args.cpu_sample_series > 0:
-        return args.cpu_sample_series
-    ns = 32
-    t = cpu_step_time(args, ns, 1)                   # dispatch-bound: cost grows slowly with lanes
-    target = 12.0
-    while ns < 128 and t * 1.7 < target:
-        ns *= 2
-        t = cpu_step_time(args, ns, 1)
-    return ns
+def cpu_sample_series(args):
+    """Series of the bounded CPU sample: a CONSTANT (the port is dispatch-bound, so its draws/s depends on the
+    sample size -- both CPU legs time the same sample)."""
+    return max(1, min(args.cpu_sample_series, args.series))
+
+
+def tfp_available():
+    """The literal reference needs tensorflow + tensorflow_probability (setup.py:51-52); probe site-packages and a
+    driver-provided install under baseline/_ref."""
+    import importlib.util
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    return all(importlib.util.find_spec(m) is not None for m in ('tensorflow', 'tensorflow_probability'))
+
+
+def run_reference_tfp(args, ns):
+    """Literal reference arm: tfp.sts.fit_with_hmc on the model the reference's build_default_model makes
+    (causalimpact/model.py:239-321,361-364) with chain_batch_shape=[chains], per series, all host threads.
+    Only reachable when TensorFlow Probability is importable (never in this image)."""
+    import tensorflow as tf
+    import tensorflow_probability as tfp
+    y, X = synth(ns, args.T, args.Tf, args.k, args.nseasons, 20245, 'cpu')
+    t_total, draws = 0.0, 0
+    for i in range(ns):
+        obs = tf.convert_to_tensor(y[i].numpy()[:, None], dtype=tf.float32)
+        comps = [tfp.sts.LocalLevel(observed_time_series=obs)]
+        if args.k:
+            comps.append(tfp.sts.SparseLinearRegression(design_matrix=tf.convert_to_tensor(X[i].numpy(), tf.float32),
+                                                        weights_prior_scale=0.1))
+        if args.nseasons > 1:
+            comps.append(tfp.sts.Seasonal(num_seasons=args.nseasons, observed_time_series=obs))
+        model = tfp.sts.Sum(comps, observed_time_series=obs)
+        t0 = time.perf_counter()
+        tfp.sts.fit_with_hmc(model, obs, num_results=args.steps, num_warmup_steps=max(args.warmup, 1),
+                             num_leapfrog_steps=LEAPFROG, chain_batch_shape=[args.chains])
+        t_total += time.perf_counter() - t0
+        draws += args.chains * args.steps
+    return draws / t_total, t_total
 
 
 def run_reference(args, rank, world):
@@ -175,22 +214,29 @@ def run_reference(args, rank, world):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    ns = cpu_calibrate(args)
-    O, prob, series, u0, step0 = cpu_setup(args, ns)
-    O.hmc_run(prob, series, u0, step0, max(args.warmup, 1), 0, LEAPFROG, 3)        # warm-up transitions
-    t0 = time.perf_counter()
-    O.hmc_run(prob, series, u0, step0, args.steps, 0, LEAPFROG, 4)
-    dt = time.perf_counter() - t0
-    draws = ns * args.chains * args.steps
-    val = draws / dt
-    sample = (f'{ns} of {args.series} series x {args.chains} chains, {args.steps} HMC transitions x {LEAPFROG} '
-              f'leapfrogs, PyTorch-CPU fp32 dense filter + autograd (TFP not installable here)')
+    ns = cpu_sample_series(args)
+    if tfp_available():
+        ns = min(ns, 8)
+        val, dt = run_reference_tfp(args, ns)
+        kind = 'reference'
+        sample = (f'{ns} of {args.series} series, tfp.sts.fit_with_hmc(num_results={args.steps}, chain_batch_shape=[{args.chains}]) '
+                  f'per series, extrapolated linearly')
+    else:
+        O, prob, series, u0, step0 = cpu_setup(args, ns)
+        O.hmc_run(prob, series, u0, step0, max(args.warmup, 1), 0, LEAPFROG, 3)        # warm-up transitions
+        t0 = time.perf_counter()
+        O.hmc_run(prob, series, u0, step0, args.steps, 0, LEAPFROG, 4)
+        dt = time.perf_counter() - t0
+        val = ns * args.chains * args.steps / dt
+        kind = 'port'
+        sample = (f'{ns} of {args.series} series x {args.chains} chains, {args.steps} HMC transitions x {LEAPFROG} '
+                  f'leapfrogs, PyTorch-CPU fp32 dense filter + autograd (tensorflow_probability probed: not importable)')
     line = {
         'impl': 'reference', 'metric': 'hmc_posterior_draws_per_sec', 'value': val, 'unit': 'draws/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, world),
-        'cpu_baseline': {'value': val, 'unit': 'draws/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'draws/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'draws/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'evals_per_sec': val * LEAPFROG, 'gpu_launches': 0,
     }
@@ -203,6 +249,140 @@ def workload_config(args, world):
             'series_per_gpu': args.series, 'chains': args.chains, 'T': args.T, 'Tf': args.Tf, 'k': args.k,
             'nseasons': args.nseasons, 'leapfrog': LEAPFROG, 'sharding': f'series x{world} (no collective)',
             'l2': 'inputs (X 0.79 GB + tape) exceed the 126 MB L2; no flush needed'}
+
+
+# ------------------------------------------------------------------------------------------------
+def fit_state(db, C, args, seed):
+    """Untimed initialisation exactly as tfp.sts.fit_with_hmc does it: mean-field VI (150 Adam steps x 5
+    samples) gives the initial state and per-coordinate step sizes, then 50 warm-up transitions with dual averaging
+    on the first 40.  Returns (state u [P,B], frozen step sizes [P,B])."""
+    mu, rho = db.vi_fit(C, args.init_vi_samples, args.init_vi_steps, 0.1, 0.01, seed=100 + seed)
+    u = db.vi_draw(mu, rho, 1, seed=200 + seed)
+    step0 = torch.nn.functional.softplus(rho).contiguous()
+    if args.init_warmup > 0:
+        _, st0 = db.hmc_run(u, step0, 0, args.init_warmup, int(0.8 * args.init_warmup), LEAPFROG, 0.75, seed=250 + seed)
+        step0 = (step0 * st0[2][None, :]).contiguous()           # freeze the adapted step sizes
+    db._ws.pop('fit', None)                                      # release the (5x larger) VI workspace
+    return u, step0
+
+
+def max_ranks(x, dist, dev):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_records(args, rank, world, dev, dist, barrier, weak_ms_per_step):
+    """The NAMED configs[3] split: `--series` series in TOTAL, contiguous blocks per rank (distributed.shard_range), all
+    chains of a series on one GPU, no data-path collective; the per-series summary rows [n, 21] are all-gathered over
+    NCCL inside the timed region.  Also the whole fit end to end (VI-init + warm-up + draws + filter +
+    forecast + summary) through batch.causal_impact_batch on the same split."""
+    from tfcausalimpact_b200 import distributed as D
+    from tfcausalimpact_b200.batch import causal_impact_batch
+    from tfcausalimpact_b200.engine import DeviceBatch, reduce_summary
+    C, T, Tf, k, S = args.chains, args.T, args.Tf, args.k, args.nseasons
+    lo, hi = D.shard_range(args.series, rank, world)
+    ns = hi - lo
+    y_pre, y_post, X, eff_true = synth(ns, T, Tf, k, S, 30244 + rank, dev, full=True)
+    db = DeviceBatch(y_pre, X if k else None, Tf=Tf, nseasons=S)
+    B = ns * C
+    u, step0 = fit_state(db, C, args, 1000 + rank)
+    # summary rows of this shard from the warm state: filter + 200 forecast samples + reduction (K6-K8)
+    pm, pv, fs = db.filter_predict(u)
+    sims, post_mean = db.forecast_sample(u, fs, 200, 77 + rank, None)
+    rows = reduce_summary(y_post, post_mean, sims, 0.05)                        # [ns, 21]
+    draws_buf = torch.empty((max(args.steps, args.warmup, 1), db.P, B), dtype=torch.float32, device=dev)
+    db.hmc_run(u, step0, max(args.warmup, 1), 0, 0, LEAPFROG, 0.75, seed=311 + rank, draws=draws_buf)
+    D.gather_series(rows, args.series)                                          # communicator warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    db.hmc_run(u, step0, args.steps, 0, 0, LEAPFROG, 0.75, seed=312 + rank, iter_offset=1000, draws=draws_buf)
+    allrows = D.gather_series(rows, args.series)
+    e1.record()
+    barrier()
+    ms = max_ranks(e0.elapsed_time(e1), dist, dev)
+    gather_ok = bool(allrows.shape[0] == args.series and torch.equal(allrows[lo:hi], rows)
+                     and torch.isfinite(allrows).all().item())
+    strong = {'scaling': 'strong', 'series_total': args.series, 'series_this_rank': ns, 'value': args.series * C * args.steps / (ms * 1e-3),
+              'unit': 'draws/s', 'ms_per_step': ms / args.steps,
+              'efficiency_vs_one_gpu': weak_ms_per_step / (world * ms / args.steps),
+              'one_gpu_ms_per_step': weak_ms_per_step,
+              'collective': f'all_gather of [{args.series},21] summary rows ({"nccl" if world > 1 else "single rank: none"}) inside the timed region',
+              'gather_ok': gather_ok, 'finite': bool(torch.isfinite(draws_buf[:args.steps]).all().item())}
+    del draws_buf, sims, db
+    torch.cuda.empty_cache()
+    # ---- the whole fit, end to end, on the same split ----
+    barrier()
+    t0 = time.perf_counter()
+    res = causal_impact_batch(y_pre, y_post, X if k else None, fit_method='hmc', nseasons=S, chains=C,
+                              num_results=args.fit_results, num_warmup=args.fit_warmup, predictive_draws=10, niter=500,
+                              seed=5 + rank, device=dev)
+    summ = D.gather_series(res['summary'].reshape(ns, 20), args.series)
+    pval = D.gather_series(res['p_value'].reshape(ns, 1), args.series)
+    barrier()
+    sec = max_ranks(time.perf_counter() - t0, dist, dev)
+    eff = summ[:, 8]                                                            # abs_effect, average column
+    full = {'seconds': sec, 'value': args.series * C * args.fit_results / sec, 'unit': 'draws/s',
+            'series_per_sec': args.series / sec,
+            'what': f'batch.causal_impact_batch on {args.series} series total over {world} GPU(s): VI init 150x5 + '
+                    f'{args.fit_warmup} warm-up + {args.fit_results} kept transitions x {C} chains, filter, 500 forecast '
+                    f'samples, summary, NCCL gather of summaries',
+            'abs_effect_mean': float(eff.mean().item()),
+            'abs_effect_true_mean': float(D.gather_series(eff_true.reshape(ns, 1), args.series).mean().item()),
+            'accept_rate': float(res['hmc_stats'][0].mean().item()),
+            'finite': bool(torch.isfinite(summ).all().item() and torch.isfinite(pval).all().item())}
+    return strong, full
+
+
+def cfg4_eval_record(dev, fp32_peak):
+    """configs[4] shape (100 series x 10,000 steps, nseasons=52, no covariates): the CTA-per-lane evaluation."""
+    from tfcausalimpact_b200.engine import DeviceBatch
+    N, T, Tf, S = 100, 10000, 520, 52
+    y, _ = synth(N, T, Tf, 0, S, 5, dev)
+    db = DeviceBatch(y, None, Tf=Tf, nseasons=S)
+    u = torch.randn(db.P, N, device=dev) * 0.3
+    lp, g = db.logp_grad(u)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        db.logp_grad(u, lp, g)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    d = S
+    flops = 3.0 * (5 * d * d + 6 * d + 16) * T * N
+    tf = flops / (ms * 1e-3) / 1e12
+    return {'workload': 'configs[4]: 100 series x 10,000 steps, nseasons=52, 1 lane per series', 'ms_per_launch': ms,
+            'algorithmic_flops_per_launch': flops, 'achieved': tf, 'unit': 'TFLOP/s', 'peak': fp32_peak,
+            'frac': tf / fp32_peak, 'finite': bool(torch.isfinite(lp).all().item() and torch.isfinite(g).all().item())}
+
+
+def h2d_ceiling(dev, dist, barrier, nbytes=256 << 20, reps=4):
+    """Plain pinned cudaMemcpyAsync host -> device, one stream per rank, all ranks at once: the box's copy ceiling the
+    e2e leg is quoted against."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    barrier()
+    ms = max_ranks(e0.elapsed_time(e1), dist, dev)
+    return nbytes * reps / (ms * 1e-3) / 1e9
+
+
+def eval_source_sha():
+    import hashlib
+    hsh = hashlib.sha256()
+    for f in ('ci_eval.cu', 'ci_eval_lane.cuh', 'ci_kalman_eff.cuh', 'ci_kalman.cuh', 'ci_params.cuh', 'ci_xstage.cuh', 'ci_core.cuh'):
+        hsh.update(open(os.path.join(ROOT, 'tfcausalimpact_b200', 'csrc', f), 'rb').read())
+    return hsh.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,16 +413,7 @@ def main():
     y, X = synth(N, T, Tf, k, S, 20244 + rank, dev)
     db = DeviceBatch(y, X if k else None, Tf=Tf, nseasons=S)
     P = db.P
-    # untimed initialisation exactly as tfp.sts.fit_with_hmc does it: mean-field VI
-    # (150 Adam steps x 5 samples) gives the initial state and per-coordinate step sizes, then 50
-    # warm-up transitions with dual averaging on the first 40
-    mu, rho = db.vi_fit(C, args.init_vi_samples, args.init_vi_steps, 0.1, 0.01, seed=100 + rank)
-    u = db.vi_draw(mu, rho, 1, seed=200 + rank)
-    step0 = torch.nn.functional.softplus(rho).contiguous()
-    if args.init_warmup > 0:
-        _, st0 = db.hmc_run(u, step0, 0, args.init_warmup, int(0.8 * args.init_warmup), LEAPFROG, 0.75, seed=250 + rank)
-        step0 = (step0 * st0[2][None, :]).contiguous()           # freeze the adapted step sizes
-    db._ws.pop('fit', None)                                      # release the (5x larger) VI workspace
+    u, step0 = fit_state(db, C, args, rank)
     draws_buf = torch.empty((max(args.steps, args.warmup, 1), P, B), dtype=torch.float32, device=dev)
 
     def barrier():
@@ -310,10 +481,13 @@ def main():
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_eval_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_eval_traffic.json')))
         wl = tj['workload']
-        if (wl['series'], wl['chains'], wl['T'], wl['k'], wl['nseasons']) == (N, C, T, k, S):
-            traffic = tj['traffic_bytes_per_launch']      # dram read + write of one launch, ncu --set full
+        # dram read + write of one launch from ONE `ncu --set full` capture (scripts/ncu_traffic.py); refused when the
+        # kernel sources changed since the capture or the workload differs
+        if (wl['series'], wl['chains'], wl['T'], wl['k'], wl['nseasons']) == (N, C, T, k, S) and \
+                tj.get('source_sha') == eval_source_sha():
+            traffic = tj['traffic_bytes_per_launch']
     except Exception:
         pass
     ach_tf = flops_per_eval / (eval_ms * 1e-3) / 1e12
@@ -370,15 +544,33 @@ def main():
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         ms_e = float(t_e.item())
+        ceil_gbs = h2d_ceiling(dev, dist, barrier)
         e2e = {'value': world * B * n_e2e / (ms_e * 1e-3), 'unit': 'draws/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'steps': n_e2e, 'ms_per_step': ms_e / n_e2e,
+               'h2d_gbs_per_rank': h2d / (ms_e / n_e2e * 1e-3) / 1e9,
+               'h2d_ceiling_gbs_per_rank': ceil_gbs,       # plain pinned cudaMemcpyAsync, all ranks at once
+               'h2d_frac_of_ceiling': h2d / (ms_e / n_e2e * 1e-3) / 1e9 / ceil_gbs,
                'api': 'engine.HostUploader (pinned host y, X, state; double-buffered) -> DeviceBatch -> hmc_run(1 transition) -> draws to pinned host'}
+
+    # ---- the named split (strong scaling) + the whole fit; configs[4] evaluation ----------------------
+    del draws_buf, lp, gr, uu
+    strong = full_fit = cfg4 = None
+    if not args.no_strong:
+        if world > 1:
+            del db
+        torch.cuda.empty_cache()
+        strong, full_fit = strong_records(args, rank, world, dev, dist, barrier, ms / args.steps)
+    if rank == 0 and not args.no_extra:
+        cfg4 = cfg4_eval_record(dev, fp32_peak)
+    if dist is not None:
+        barrier()
 
     # ---- CPU baseline (rank 0 only, N=1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        ns = cpu_calibrate(args)
+        ns = cpu_sample_series(args)
+        cpu_step_time(args, ns, 1, seed=8)            # warm-up transition (thread pool, allocator)
         t = cpu_step_time(args, ns, 2, seed=9)
         cpu = {'value': ns * C / t, 'unit': 'draws/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': f'{ns} of {N} series x {C} chains, 2 HMC transitions x {LEAPFROG} leapfrogs, PyTorch-CPU '
@@ -390,7 +582,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, world), 'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches,
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'roofline': roofline, 'cpu_baseline': cpu, 'strong': strong, 'full_fit': full_fit, 'configs4_eval': cfg4,
             'evals_per_sec': draws_per_s * LEAPFROG, 'eval_only_evals_per_sec_per_gpu': B / (eval_ms * 1e-3),
             'accept_rate': accept, 'finite': finite,
         }
