@@ -133,6 +133,28 @@ def test_summary_matches_reference_goldens(summary_data):
     assert 'p = ' in summarizer.summary(summary_data, 0.03, output='report')
 
 
+REPORT_CASES = [
+    # golden, rel_effect, lower, upper, alpha, p_value, digits   (reference tests/test_summary.py:78-151)
+    ('test_report_summary_1', 0.41, -0.30, 0.30, 0.1, 0.5, 2),           # positive, not significant
+    ('test_report_summary_2', 0.41, 0.434, 0.234, 0.1, 0.05, 2),         # positive, significant
+    ('test_report_summary_3', -0.343, -0.434, 0.234, 0.1, 0.5, 2),       # negative, not significant
+    ('test_report_summary_4', -0.343, -0.434, -0.234, 0.1, 0.05, 2),     # negative, significant
+    ('test_report_summary_single_digit', 0.41, -0.30, 0.30, 0.1, 0.5, 1),
+]
+
+
+@pytest.mark.parametrize('golden,rel,lo,hi,alpha,p,digits', REPORT_CASES)
+def test_report_matches_reference_goldens(summary_data, golden, rel, lo, hi, alpha, p, digits):
+    """`summary(output='report')` byte for byte against the reference's five report goldens
+    (/root/reference/tests/fixtures/test_report_summary_*, templates/report:1-81)."""
+    summary_data = summary_data.copy()
+    summary_data.loc['rel_effect', 'average'] = rel
+    summary_data.loc['rel_effect_lower', 'average'] = lo
+    summary_data.loc['rel_effect_upper', 'average'] = hi
+    exp = open(os.path.join(GOLD, golden)).read().strip()
+    assert summarizer.summary(summary_data, p, alpha=alpha, output='report', digits=digits) == exp
+
+
 def test_default_model_spec(rand_data):
     data = cidata.format_input_data(rand_data)
     pre, post = cidata.process_pre_post_data(data, [0, 99], [100, 199])
@@ -207,3 +229,112 @@ def test_no_cpu_fallback(monkeypatch):
     from tfcausalimpact_b200.engine import DeviceBatch
     with pytest.raises(_native.NativeError):
         DeviceBatch(np.zeros((1, 10), np.float32))
+
+
+@pytest.mark.parametrize('freq,hole,expect_len', [
+    ('MS', 7, 24),        # month starts, one missing month -> exactly one NaN row (was re-gridded at 28 days)
+    ('QS', 3, 12),        # quarter starts
+    ('YS', 2, 8),         # year starts
+    ('ME', 5, 24),        # month ends
+    ('D', 10, 40),        # daily
+    ('h', 10, 40),        # hourly
+    ('W-SUN', 4, 20),     # weekly
+])
+def test_regularize_series_calendar_steps_with_a_hole(freq, hole, expect_len):
+    idx = pd.date_range('2015-01-01', periods=expect_len, freq=freq)
+    df = pd.DataFrame({'y': np.arange(expect_len, dtype=float)}, index=idx).drop(idx[hole])
+    assert df.index.freq is None
+    out = cidata.regularize_series(df)
+    assert len(out) == expect_len and out.index.equals(idx)
+    assert int(out['y'].isna().sum()) == 1 and np.isnan(out['y'].iloc[hole])
+    assert out['y'].notna().sum() == df['y'].notna().sum()
+
+
+def test_regularize_series_business_days_and_irregular_stamps():
+    bd = pd.bdate_range('2020-01-06', periods=10)                     # Mon-Fri x 2: smallest gap = 1 day
+    out = cidata.regularize_series(pd.DataFrame({'y': np.arange(10.0)}, index=pd.DatetimeIndex(bd.values)))
+    assert len(out) == 12 and int(out['y'].isna().sum()) == 2          # the week-end becomes two masked steps
+    irr = pd.DatetimeIndex(['2020-01-01 00:00', '2020-01-01 00:07', '2020-01-01 00:17', '2020-01-01 01:00'])
+    df = pd.DataFrame({'y': [1.0, 2.0, 3.0, 4.0]}, index=irr)
+    with pytest.warns(RuntimeWarning):
+        out = cidata.regularize_series(df)
+    assert out is df                                                   # never drops observations silently
+
+
+def _batch_frames(N=5, T=40, gap=(7, 33)):
+    rng = np.random.default_rng(2)
+    full = pd.date_range('2020-01-01', periods=T, freq='D')
+    keep = np.ones(T, dtype=bool)
+    keep[list(gap)] = False
+    idx = pd.DatetimeIndex(full[keep].values)
+    return [pd.DataFrame(rng.normal(size=(keep.sum(), 3)), index=idx, columns=['y', 'a', 'b']) for _ in range(N)], full
+
+
+def test_process_batch_input_groups_gaps_and_periods():
+    """Vectorised front door: one group per shared index, date periods resolved once, gaps -> NaN rows
+    of every series; equal to the single-series `process_input_data` slices."""
+    from tfcausalimpact_b200.batch_input import process_batch_input
+    frames, full = _batch_frames()
+    odd = frames[0].copy()
+    odd.index = pd.DatetimeIndex(odd.index.values) + pd.Timedelta(days=0)      # equal but distinct index object
+    other = pd.DataFrame(np.random.default_rng(3).normal(size=(40, 3)), index=full, columns=['y', 'a', 'b'])
+    proc = process_batch_input(frames + [odd, other], ['2020-01-01', '2020-01-30'], ['2020-01-31', '2020-02-09'])
+    assert proc['n'] == 7 and len(proc['groups']) == 2
+    g = proc['groups'][0]
+    assert list(g.positions) == [0, 1, 2, 3, 4, 5]
+    y_pre, y_post, X = (t.numpy() for t in g.tensors('cpu'))            # the same torch code runs on the device
+    assert y_pre.shape == (6, 30) and y_post.shape == (6, 10) and X.shape == (6, 40, 2)
+    assert np.isnan(y_pre[:, 7]).all() and np.isnan(y_post[:, 3]).all() and np.isnan(X[:, 7]).all()
+    ref = cidata.process_input_data(frames[2], ['2020-01-01', '2020-01-30'], ['2020-01-31', '2020-02-09'], None,
+                                    {'standardize': False}, 0.05)
+    np.testing.assert_allclose(y_pre[2], ref['pre_data'].iloc[:, 0].values, rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(y_post[2], ref['post_data'].iloc[:, 0].values, rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(X[2, :30], ref['pre_data'].iloc[:, 1:].values, rtol=1e-6, equal_nan=True)
+    assert g.pre_index.equals(ref['pre_data'].index) and g.post_index.equals(ref['post_data'].index)
+    y1 = proc['groups'][1].tensors('cpu')[0].numpy()
+    assert y1.shape == (1, 30) and not np.isnan(y1).any()
+
+
+def test_process_batch_input_errors_name_the_series():
+    from tfcausalimpact_b200.batch_input import BatchInputError
+    from tfcausalimpact_b200 import batch_input
+
+    def process_batch_input(*a):                    # periods / stacking on the host, per-series checks where the block lives
+        proc = batch_input.process_batch_input(*a)
+        for g in proc['groups']:
+            g.tensors('cpu')
+        return proc
+    frames, _ = _batch_frames()
+    pre, post = ['2020-01-01', '2020-01-30'], ['2020-01-31', '2020-02-09']
+    bad = [f.copy() for f in frames]
+    bad[3].iloc[:, 0] = 1.0
+    with pytest.raises(BatchInputError) as e:
+        process_batch_input(bad, pre, post)
+    assert str(e.value) == 'Input response cannot be constant.' and e.value.series == 3
+    bad = [f.copy() for f in frames]
+    bad[1].iloc[4, 2] = np.nan
+    with pytest.raises(ValueError) as e:
+        process_batch_input(bad, pre, post)
+    assert str(e.value) == 'Input data cannot have NAN values.' and e.value.series == 1
+    bad = [f.copy() for f in frames]
+    bad[2].iloc[:, 0] = np.nan
+    with pytest.raises(ValueError) as e:
+        process_batch_input(bad, pre, post)
+    assert str(e.value) == 'Input response cannot have just Null values.'
+    bad = [f.copy().astype(object) for f in frames[:2]]
+    bad[1].iloc[0, 1] = 'x'
+    with pytest.raises(ValueError) as e:
+        process_batch_input(bad, pre, post)
+    assert str(e.value) == 'Input data must contain only numeric values.' and e.value.series == 1
+    with pytest.raises(ValueError) as e:
+        process_batch_input(frames, pre, ['2020-01-30', '2020-02-09'])
+    assert 'Values in training data' in str(e.value) or 'post_period first value' in str(e.value)
+    with pytest.raises(ValueError) as e:
+        process_batch_input(frames, pre, ['2020-03-30', '2020-04-09'])
+    assert str(e.value) == '2020-03-30 not present in input data index.'
+    arr = np.random.default_rng(0).normal(size=(4, 30, 2)).astype(np.float32)
+    proc = process_batch_input(arr, [0, 19], [20, 29])
+    assert proc['groups'][0].tensors('cpu')[0].shape == (4, 20) and proc['groups'][0].range_index
+    with pytest.raises(ValueError) as e:
+        process_batch_input(arr, [0, 1], [20, 29])
+    assert str(e.value) == 'pre_period must span at least 3 time points.'

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import distributed as D
-from .engine import DeviceBatch, reduce_summary
+from .engine import DeviceBatch, reduce_inferences, reduce_summary
 
 SUMMARY_ROWS = ['actual', 'predicted', 'predicted_lower', 'predicted_upper', 'abs_effect', 'abs_effect_lower',
                 'abs_effect_upper', 'rel_effect', 'rel_effect_lower', 'rel_effect_upper']
@@ -16,25 +16,31 @@ SUMMARY_ROWS = ['actual', 'predicted', 'predicted_lower', 'predicted_upper', 'ab
 
 def standardize_batch(y_pre, y_post, X):
     """Per-series standardisation by PRE-period statistics of every column (data.py:206-229,
-    misc.py:27-54: population std, NaN-aware).  Returns standardised tensors and mu_sig [2, N]."""
+    misc.py:27-54: population std, NaN-aware).  Returns standardised tensors and mu_sig [2, N].
+    Covariate rows inserted by the gap regularisation are NaN on input and 0 afterwards, and a covariate that is
+    constant over the pre-period (a dummy that switches on with the intervention: std 0 -> NaN / inf) becomes 0 as
+    well -- the reference zero-fills the standardised design matrix the same way (model.py:303-308)."""
     T = y_pre.shape[1]
     m = torch.nanmean(y_pre, dim=1, keepdim=True)
     sd = torch.sqrt(torch.nanmean((y_pre - m) ** 2, dim=1, keepdim=True))
     ys_pre, ys_post = (y_pre - m) / sd, (y_post - m) / sd
     Xs = None
     if X is not None:
-        xm = X[:, :T].mean(dim=1, keepdim=True)
-        xs = X[:, :T].std(dim=1, unbiased=False, keepdim=True)
-        Xs = (X - xm) / xs
+        xm = torch.nanmean(X[:, :T], dim=1, keepdim=True)
+        xs = torch.sqrt(torch.nanmean((X[:, :T] - xm) ** 2, dim=1, keepdim=True))
+        Xs = torch.nan_to_num((X - xm) / xs, nan=0.0, posinf=0.0, neginf=0.0)
     return ys_pre, ys_post, Xs, torch.cat([m.t(), sd.t()], dim=0).contiguous()
 
 
 def causal_impact_batch(y_pre, y_post, X=None, fit_method='vi', nseasons=1, season_duration=1,
                         prior_level_sd=0.01, standardize=True, niter=1000, alpha=0.05, chains=1,
-                        num_results=100, num_warmup=50, predictive_draws=None, seed=0, device=None):
+                        num_results=100, num_warmup=50, predictive_draws=None, seed=0, device=None,
+                        return_inferences=False):
     """y_pre [N,T], y_post [N,Tf] (NaN = missing), X [N,T+Tf,k] or None -> dict with
     'summary' [N,10,2] (rows SUMMARY_ROWS; columns average, cumulative), 'p_value' [N] and the
-    posterior draws in unconstrained space.  Under torchrun the series are sharded over ranks and
+    posterior draws in unconstrained space; with `return_inferences` also 'inferences' [N,16,T+Tf+1], the
+    16 columns of the reference's inference frame (inferences.py:208-246; masked post steps compacted to the
+    front, as `ci_reduce_inferences` lays them out).  Under torchrun the series are sharded over ranks and
     the summaries gathered; inputs are then this rank's shard."""
     dev = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
     y_pre = torch.as_tensor(y_pre, dtype=torch.float32, device=dev)
@@ -43,7 +49,7 @@ def causal_impact_batch(y_pre, y_post, X=None, fit_method='vi', nseasons=1, seas
     N, T = y_pre.shape
     Tf = y_post.shape[1]
     mu_sig = None
-    ys_pre, Xs = y_pre, X
+    ys_pre, Xs = y_pre, (None if X is None else torch.nan_to_num(X, nan=0.0))
     if standardize:
         ys_pre, _, Xs, mu_sig = standardize_batch(y_pre, y_post, X)
     db = DeviceBatch(ys_pre, Xs, Tf=Tf, nseasons=nseasons, season_duration=season_duration,
@@ -66,9 +72,17 @@ def causal_impact_batch(y_pre, y_post, X=None, fit_method='vi', nseasons=1, seas
         raise ValueError('fit_method can be either "hmc" or "vi".')
     pm, pv, fs = db.filter_predict(u)
     sims, post_mean = db.forecast_sample(u, fs, niter, seed + 3, mu_sig)
+    inferences = None
+    if return_inferences:
+        # a first set of predictive samples feeds the 16-column frame, a FRESH set of forecast trajectories the
+        # summary table and p-value -- as the reference does (inferences.py:108-117, main.py:377)
+        pre_sims, pre_mean = db.onestep_sample(pm, pv, niter, seed + 4, mu_sig)
+        inferences = reduce_inferences(y_pre, y_post, pre_sims, pre_mean, sims, post_mean, alpha)
+        del pre_sims
+        sims, post_mean = db.forecast_sample(u, fs, niter, seed + 5, mu_sig)
     out = reduce_summary(y_post, post_mean, sims, alpha)                        # [N, 21]
     return {'summary': out[:, :20].reshape(N, 10, 2), 'p_value': out[:, 20], 'u_draws': u,
-            'hmc_stats': stats, 'mu_sig': mu_sig, 'engine': db}
+            'hmc_stats': stats, 'mu_sig': mu_sig, 'engine': db, 'inferences': inferences}
 
 
 def causal_impact_sharded(y_pre, y_post, X=None, **kw):

@@ -27,6 +27,7 @@ def process_input_data(data, pre_period, post_period, model, model_args, alpha) 
     mask = _build_nan_mask(post_data)
     alpha = process_alpha(alpha)
     model_args = cimodel.process_model_args(model_args if model_args else {})
+    cimodel.check_capability_limits(model_args)
     if model_args['standardize']:
         normed_pre, normed_post, mu_sig = standardize_pre_and_post_data(pre_data, post_data)
     else:
@@ -90,33 +91,67 @@ def format_input_data(data) -> pd.DataFrame:
     return data.astype(np.float32)
 
 
-def regularize_series(frame: pd.DataFrame) -> pd.DataFrame:
-    """Re-index on a regular grid, NaN where the input had gaps.
+def _infer_step(idx: pd.DatetimeIndex):
+    """Grid step of a DatetimeIndex the way `tfp.sts.regularize_series` infers it (documented behaviour: the
+    smallest distance between consecutive observations, with months and years treated as calendar units):
+    the index's own `freq` if it carries one; else, when every stamp falls on the same day-of-month (or every
+    stamp is a month end) at the same time of day, the smallest month distance as a calendar offset; else the
+    smallest positive gap as a fixed-length step.  `pd.infer_freq` is deliberately NOT used: it returns
+    business-day / anchored frequencies ('B', 'W-SUN', ...) that would hide gaps the smallest-gap rule fills
+    with NaN (a Mon-Fri index gets NaN week-ends, as with TFP)."""
+    if idx.freq is not None:
+        return idx.freq
+    gaps = np.diff(idx.values)
+    pos = gaps[gaps > np.timedelta64(0)]
+    if len(pos) == 0:
+        return None
+    same_clock = bool((idx.normalize() + (idx[0] - idx[0].normalize()) == idx).all())
+    months = np.diff(idx.year.values * 12 + idx.month.values)
+    if same_clock and (months > 0).any() and pd.Timedelta(pos.min()) >= pd.Timedelta(days=28):
+        m = int(months[months > 0].min())
+        if bool((months % m == 0).all()):
+            if bool((idx.day == idx[0].day).all()):
+                return pd.DateOffset(years=m // 12) if m % 12 == 0 else pd.DateOffset(months=m)
+            if bool(idx.is_month_end.all()):
+                return pd.offsets.MonthEnd(m)
+    step = pd.Timedelta(pos.min())
+    return pd.DateOffset(days=step.days) if step == pd.Timedelta(days=step.days) and step.days > 0 else step
 
-    Stand-in for `tfp.sts.regularize_series`: use the index's own frequency, else pandas'
-    inferred one, else the smallest positive gap between consecutive stamps."""
+
+def regularize_series(frame: pd.DataFrame) -> pd.DataFrame:
+    """Re-index on a regular grid, NaN where the input had gaps (stand-in for
+    `tfp.sts.regularize_series`, /root/reference/causalimpact/data.py:333-334).  If the inferred grid would
+    DROP observations (stamps that are not multiples of the step) the frame is returned unchanged with a
+    warning instead of silently fitting a mostly-NaN series."""
     idx = frame.index
     if not isinstance(idx, pd.DatetimeIndex) or len(idx) < 2:
         return frame
-    freq = idx.freq
-    if freq is None:
-        try:
-            freq = pd.infer_freq(idx) if len(idx) >= 3 else None
-        except (TypeError, ValueError):
-            freq = None
-    if freq is None:
-        gaps = np.diff(idx.values)
-        gaps = gaps[gaps > np.timedelta64(0)]
-        if len(gaps) == 0:
-            return frame
-        step = pd.Timedelta(gaps.min())
-        freq = pd.DateOffset(days=step.days) if step == pd.Timedelta(days=step.days) and step.days > 0 else step
-    return frame.asfreq(freq)
+    step = _infer_step(idx)
+    if step is None:
+        return frame
+    out = frame.asfreq(step)
+    if int(out.iloc[:, 0].notna().sum()) < int(frame.iloc[:, 0].notna().sum()):
+        import warnings
+        warnings.warn('regularize_series: the time index is not a regular grid with gaps (step '
+                      f'{step} would drop observations); the series is used as given.', RuntimeWarning)
+        return frame
+    return out
 
 
 def process_pre_post_data(data: pd.DataFrame, pre_period, post_period) -> List[pd.DataFrame]:
     pre = process_period(pre_period, data)
     post = process_period(post_period, data)
+    check_periods(pre, post, pre_period, post_period)
+    if isinstance(data.index, pd.RangeIndex):
+        # the state-space model needs a calendar: synthesise a daily one
+        data = data.set_index(pd.date_range(start='2020-01-01', periods=len(data)))
+    pre_data = data.iloc[pre[0]: pre[1] + 1, :]
+    post_data = data.iloc[post[0]: post[1] + 1, :]
+    return [regularize_series(pre_data), regularize_series(post_data)]
+
+
+def check_periods(pre: List[int], post: List[int], pre_period, post_period) -> None:
+    """Consistency rules of the two periods as integer positions (data.py:360-385 of the reference)."""
     if pre[1] > post[0]:
         raise ValueError(
             'Values in training data cannot be present in the post-intervention '
@@ -132,12 +167,6 @@ def process_pre_post_data(data: pd.DataFrame, pre_period, post_period) -> List[p
         raise ValueError(f'post_period first value ({post_period[0]}) must '
                          'be bigger than the second value of pre_period '
                          f'({pre_period[1]}).')
-    if isinstance(data.index, pd.RangeIndex):
-        # the state-space model needs a calendar: synthesise a daily one
-        data = data.set_index(pd.date_range(start='2020-01-01', periods=len(data)))
-    pre_data = data.iloc[pre[0]: pre[1] + 1, :]
-    post_data = data.iloc[post[0]: post[1] + 1, :]
-    return [regularize_series(pre_data), regularize_series(post_data)]
 
 
 def validate_y(y: pd.Series) -> None:

@@ -74,19 +74,28 @@ def compile_posterior_inferences(original_index, mask, pre_data: pd.DataFrame, p
     post_sims, post_mean = _samples(posterior_dist, niter, mu_sig, dev, Tf)
     out = engine.reduce_inferences(y_pre, y_post, pre_sims[None], pre_mean[None], post_sims[None],
                                    post_mean[None], float(alpha))[0].cpu().numpy().astype(np.float64)
-    post_masked = post_data[mask]
-    nvalid = int(mask.sum())
-    full_index = pre_data.index.append(post_masked.index)
-    cum_index = build_cum_index(pre_data.index, post_masked.index)
+    return frame_from_reduction(out, mask, pre_data.index, post_data.index, isinstance(original_index, pd.RangeIndex))
+
+
+def frame_from_reduction(out: np.ndarray, mask: np.ndarray, pre_index: pd.Index, post_index: pd.Index,
+                         range_index: bool) -> pd.DataFrame:
+    """[16, T + Tf + 1] device reduction (masked post steps compacted to the front) -> the reference's 16-column
+    frame: complete / point-effect columns over pre + observed post labels, post columns over observed post labels,
+    cumulative columns prefixed by a 0 at the last pre label (inferences.py:208-282)."""
+    T = len(pre_index)
+    post_masked = post_index[np.asarray(mask, dtype=bool)]
+    nvalid = len(post_masked)
+    full_index = pre_index.append(post_masked)
+    cum_index = build_cum_index(pre_index, post_masked)
     frame = pd.DataFrame(np.nan, index=full_index, columns=COLUMNS, dtype=np.float64)
     for c, name in enumerate(COLUMNS):
         if c in _COMPLETE:
             frame[name] = out[c, :T + nvalid]
         elif c in _POST:
-            frame.loc[post_masked.index, name] = out[c, :nvalid]
+            frame.loc[post_masked, name] = out[c, :nvalid]
         else:
             frame.loc[cum_index, name] = out[c, :nvalid + 1]
-    if isinstance(original_index, pd.RangeIndex):
+    if range_index:
         frame.set_index(pd.RangeIndex(start=0, stop=len(frame)), inplace=True)
     return frame
 

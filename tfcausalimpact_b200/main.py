@@ -45,46 +45,57 @@ class CausalImpact:
 
     @staticmethod
     def batch(data, pre_period, post_period, model_args: Dict[str, Any] = {}, alpha: float = 0.05,
-              chains: int = 1, seed: int = 0):
-        """Many same-shaped series in ONE pass on the GPU (the reference can only
-        loop over `CausalImpact(...)` calls).
+              chains: int = 1, seed: int = 0, series_col: Optional[str] = None, time_col: Optional[str] = None,
+              inferences: bool = False, max_series_per_pass: Optional[int] = None):
+        """Many series in ONE pass on the GPU (the reference can only loop over
+        `CausalImpact(...)` calls, each paying its own pandas preprocessing).
 
-        data: array [N, T_total, 1 + k] (column 0 = response, the rest covariates; NaN in the response
-        marks missing steps); pre_period / post_period: integer [first, last] positions, inclusive,
-        shared by all series; model_args / alpha as for the constructor (same validation and errors).
-        Returns a `BatchResult`."""
+        data: array [N, T_total, 1 + k] (column 0 = response, the rest covariates; NaN in the response marks
+        missing steps)  |  a sequence of N DataFrames (any mix of indexes; series sharing an index are processed
+        as one block)  |  a long-format DataFrame with `series_col` (and `time_col`).  pre_period / post_period:
+        `[first, last]` as int positions, date strings or Timestamps, resolved against every index exactly as the
+        constructor does (same validation, same error strings; `batch_input.BatchInputError.series` names the
+        offending series).  Gaps in a DatetimeIndex become masked steps (data.py:333-334).  model_args / alpha as
+        for the constructor.  `inferences=True` also returns the 16-column inference frames
+        (`BatchResult.inferences_frame(i)`).  Returns a `BatchResult`."""
         from .batch import causal_impact_batch
-        arr = np.asarray(data, dtype=np.float32)
-        if arr.ndim != 3 or arr.shape[0] < 1:
-            raise ValueError('data must be an array of shape [N, T, 1 + k].')
+        from .batch_input import process_batch_input
         alpha = cidata.process_alpha(alpha)
         args = cimodel.process_model_args(dict(model_args) if model_args else {})
-        frame = pd.DataFrame(arr[0])
-        pre, post = cidata.process_period(pre_period, frame), cidata.process_period(post_period, frame)
-        if pre[1] > post[0]:
-            raise ValueError('Values in training data cannot be present in the post-intervention '
-                             'data. Please fix your pre_period value to cover at most one point less '
-                             'from when the intervention happened.')
-        if pre[1] - pre[0] < 3:
-            raise ValueError('pre_period must span at least 3 time points.')
-        if post[1] < post[0]:
-            raise ValueError('post_period last number must be bigger than its first.')
-        if post[0] <= pre[1]:
-            raise ValueError(f'post_period first value ({post_period[0]}) must '
-                             'be bigger than the second value of pre_period '
-                             f'({pre_period[1]}).')
-        if arr.shape[2] > 1 and np.isnan(arr[:, :, 1:]).any():
-            raise ValueError('Input data cannot have NAN values.')
-        y_pre, y_post = arr[:, pre[0]:pre[1] + 1, 0], arr[:, post[0]:post[1] + 1, 0]
-        X = None
-        if arr.shape[2] > 1:
-            X = np.concatenate([arr[:, pre[0]:pre[1] + 1, 1:], arr[:, post[0]:post[1] + 1, 1:]], axis=1)
-        res = causal_impact_batch(np.ascontiguousarray(y_pre), np.ascontiguousarray(y_post), X,
-                                  fit_method=args['fit_method'], nseasons=args['nseasons'],
-                                  season_duration=args['season_duration'], prior_level_sd=args['prior_level_sd'],
-                                  standardize=args['standardize'], niter=args['niter'], alpha=alpha, chains=chains,
-                                  seed=seed)
-        return BatchResult(res['summary'].cpu().numpy(), res['p_value'].cpu().numpy(), alpha, args)
+        cimodel.check_capability_limits(args)
+        from . import _native as nt
+        nt.require_cuda()
+        dev = torch.device(f'cuda:{torch.cuda.current_device()}')
+        proc = process_batch_input(data, pre_period, post_period, series_col, time_col)
+        n = proc['n']
+        summ = np.empty((n, 10, 2), dtype=np.float32)
+        pval = np.empty((n,), dtype=np.float32)
+        infs: List[Any] = [None] * n if inferences else None
+        group_of = np.empty((n,), dtype=np.int64)
+        for gi, g in enumerate(proc['groups']):
+            T, Tf, _ = g.shape_key
+            step = max_series_per_pass
+            if step is None:          # bound the [n, niter, T] one-step sample tensor of the inference path
+                step = max(1, int(6e9 // (4 * args['niter'] * max(T, 1)))) if inferences else len(g.positions)
+            for lo in range(0, len(g.positions), step):
+                sl = slice(lo, min(lo + step, len(g.positions)))
+                y_pre, y_post, X = g.tensors(dev, sl.start, sl.stop)
+                res = causal_impact_batch(y_pre, y_post, X,
+                                          fit_method=args['fit_method'], nseasons=args['nseasons'],
+                                          season_duration=args['season_duration'],
+                                          prior_level_sd=args['prior_level_sd'], standardize=args['standardize'],
+                                          niter=args['niter'], alpha=alpha, chains=chains, seed=seed + lo,
+                                          return_inferences=inferences, device=dev)
+                pos = g.positions[sl]
+                summ[pos] = res['summary'].cpu().numpy()
+                pval[pos] = res['p_value'].cpu().numpy()
+                group_of[pos] = gi
+                if inferences:
+                    arr = res['inferences'].cpu().numpy()
+                    present = (~torch.isnan(y_post)).cpu().numpy()
+                    for j, p_ in enumerate(pos):
+                        infs[p_] = (arr[j], present[j])
+        return BatchResult(summ, pval, alpha, args, infs, proc['groups'], group_of, proc['labels'])
 
     def plot(self, panels: List[str] = ['original', 'pointwise', 'cumulative'], figsize: Tuple[int] = (10, 7),
              show: bool = True) -> None:
@@ -130,13 +141,17 @@ class CausalImpact:
 
 
 class BatchResult:
-    """Per-series summary tables and tail-area p-values of `CausalImpact.batch`."""
+    """Per-series summary tables, tail-area p-values and (optionally) inference frames of `CausalImpact.batch`."""
 
-    def __init__(self, summary: np.ndarray, p_values: np.ndarray, alpha: float, model_args: Dict[str, Any]):
+    def __init__(self, summary: np.ndarray, p_values: np.ndarray, alpha: float, model_args: Dict[str, Any],
+                 inferences=None, groups=None, group_of=None, labels=None):
         self._summary = summary            # [N, 10, 2]
         self.p_values = p_values           # [N]
         self.alpha = alpha
         self.model_args = model_args
+        self._inferences = inferences      # per series: ([16, T + Tf + 1] array, post-period mask) or None
+        self._groups, self._group_of = groups, group_of
+        self.labels = labels               # series labels of a long-format input
 
     def __len__(self):
         return self._summary.shape[0]
@@ -149,9 +164,18 @@ class BatchResult:
     def summary(self, i: int, output: str = 'summary', digits: int = 2) -> str:
         return summarizer.summary(self.summary_data(i), float(self.p_values[i]), self.alpha, output, digits)
 
+    def inferences_frame(self, i: int) -> pd.DataFrame:
+        """The 16-column inference frame of series i, indexed and laid out like `CausalImpact.inferences`
+        (inferences.py:208-249: masked post steps dropped, cumulative columns prefixed at the last pre label)."""
+        if self._inferences is None:
+            raise ValueError('CausalImpact.batch was called without inferences=True.')
+        out, mask = self._inferences[i]
+        g = self._groups[int(self._group_of[i])]
+        return inferrer.frame_from_reduction(out.astype(np.float64), mask, g.pre_index, g.post_index, g.range_index)
+
     def to_frame(self) -> pd.DataFrame:
         """One row per series: the 'average' column of every summary row, the cumulative effect and p."""
         cols = {name: self._summary[:, r, 0] for r, name in enumerate(inferrer.SUMMARY_INDEX)}
         cols['cum_abs_effect'] = self._summary[:, 4, 1]
         cols['p_value'] = self.p_values
-        return pd.DataFrame(cols)
+        return pd.DataFrame(cols, index=self.labels)

@@ -55,6 +55,23 @@ def process_model_args(model_args: Dict[str, Any]) -> Dict[str, Any]:
     return model_args
 
 
+MAX_NITER = 8192          # draws one sorting CTA of ci_reduce_inferences / ci_reduce_summary holds (csrc/ci_reduce.cu)
+MAX_LATENT = 96           # latent size (1 + nseasons [+ trend slope]) of the shared-memory filter (csrc/ci_bigd.cu)
+
+
+def check_capability_limits(model_args: Dict[str, Any]) -> None:
+    """Limits of this implementation that the reference does not have, reported BEFORE any fitting with a clear
+    message (the C-ABI would return CI_ERR_UNSUPPORTED only after the fit has run)."""
+    if model_args['niter'] > MAX_NITER:
+        raise ValueError(f'niter={model_args["niter"]} exceeds the {MAX_NITER} posterior-predictive samples '
+                         'this implementation supports.')
+    if model_args['niter'] < 1:
+        raise ValueError('niter must be at least 1.')
+    if 1 + model_args['nseasons'] > MAX_LATENT:
+        raise ValueError(f'nseasons={model_args["nseasons"]} exceeds the {MAX_LATENT - 1} seasons this '
+                         'implementation supports (latent size 1 + nseasons <= 96).')
+
+
 # ------------------------------------------------------------------------------------------------
 # Spec objects (attribute names follow what the reference's tests / notebook introspect:
 # model.components[i], .design_matrix.to_dense(), .num_seasons, .num_steps_per_season,

@@ -2,7 +2,8 @@
 
 `summary(..., output='summary')` reproduces the reference's table layout byte for byte
 (/root/reference/causalimpact/summary/templates/summary, golden files under tests/golden/).
-`output='report'` gives a short prose interpretation written for this package.
+`output='report'` reproduces the reference's report wording (templates/report), pinned by the five
+report goldens of the reference's test-suite.
 """
 import pandas as pd
 
@@ -65,26 +66,85 @@ def _render_summary(s, alpha, z, p_value, digits):
 
 
 def _render_report(s, alpha, p_value, digits):
+    """The reference's prose report (wording, paragraph variants and rounding of
+    /root/reference/causalimpact/summary/templates/report:1-81; pinned byte for byte by the five
+    tests/golden/test_report_summary_* files of the reference's test-suite).
+    Significance follows the reference: the (1 - alpha) interval of the relative effect excludes 0
+    (`detected_sig`), sign of the relative effect (`positive_sig`); the p-value only selects the closing
+    paragraph."""
     a, c = s['average'], s['cumulative']
     r = lambda v: round(float(v), digits)   # noqa: E731
-    ci = int(round((1 - alpha) * 100))
-    sig = p_value < alpha
-    direction = 'increase' if a['rel_effect'] > 0 else 'decrease'
-    out = [
-        'Analysis report {CausalImpact}', '',
-        f'During the post-intervention period the response averaged {r(a["actual"])}; without the '
-        f'intervention the model expected {r(a["predicted"])} ({ci}% interval [{r(a["predicted_lower"])}, '
-        f'{r(a["predicted_upper"])}]). The estimated effect on the average is {r(a["abs_effect"])} '
-        f'({ci}% interval [{r(a["abs_effect_lower"])}, {r(a["abs_effect_upper"])}]).', '',
-        f'Summed over the post-intervention period the response was {r(c["actual"])} against an expected '
-        f'{r(c["predicted"])} ({ci}% interval [{r(c["predicted_lower"])}, {r(c["predicted_upper"])}]).', '',
-        f'In relative terms this is a {direction} of {r(a["rel_effect"] * 100)}% ({ci}% interval '
-        f'[{r(a["rel_effect_lower"] * 100)}%, {r(a["rel_effect_upper"] * 100)}%]).', '',
-        f'The posterior tail-area probability is p = {round(float(p_value), max(digits, 3))}: the effect is '
-        + ('statistically significant and unlikely to be due to random fluctuation.' if sig else
-           'not statistically significant and may be the result of random fluctuation.'),
+    detected = not (a['rel_effect_lower'] < 0 and a['rel_effect_upper'] > 0)
+    positive = a['rel_effect'] > 0
+    ci = str((1 - alpha) * 100).rstrip('0').rstrip('.') + '%'
+    rel = [r(100 * a['rel_effect_lower']), r(100 * a['rel_effect_upper'])]
+    p = [
+        'Analysis report {CausalImpact}\n\n\n'
+        'During the post-intervention period, the response variable had\n'
+        f'an average value of approx. {r(a["actual"])}. {"By contrast, in" if detected else "In"} the absence of an\n'
+        f'intervention, we would have expected an average response of {r(a["predicted"])}.\n'
+        f'The {ci} interval of this counterfactual prediction is [{r(a["predicted_lower"])}, {r(a["predicted_upper"])}].\n'
+        'Subtracting this prediction from the observed response yields\n'
+        'an estimate of the causal effect the intervention had on the\n'
+        f'response variable. This effect is {r(a["abs_effect"])} with a {ci} interval of\n'
+        f'{sorted([r(a["abs_effect_lower"]), r(a["abs_effect_upper"])])}. For a discussion of the significance of this effect,\n'
+        'see below.\n\n\n'
+        'Summing up the individual data points during the post-intervention\n'
+        'period (which can only sometimes be meaningfully interpreted), the\n'
+        f'response variable had an overall value of {r(c["actual"])}.\n'
+        f'{"By contrast, had" if detected else "Had"} the intervention not taken place, we would have expected\n'
+        f'a sum of {r(c["predicted"])}. The {ci} interval of this prediction is '
+        f'{sorted([r(c["predicted_lower"]), r(c["predicted_upper"])])}.\n\n\n'
+        'The above results are given in terms of absolute numbers. In relative\n'
+        f'terms, the response variable showed {"an increase of +" if positive else "a decrease of "}'
+        f'{r(100 * a["rel_effect"])}%. The {ci}\n'
+        f'interval of this percentage is [{min(rel)}%, {max(rel)}%].\n'
     ]
-    return '\n'.join(out)
+    if detected and positive:
+        p.append('\n\nThis means that the positive effect observed during the intervention\n'
+                 'period is statistically significant and unlikely to be due to random\n'
+                 'fluctuations. It should be noted, however, that the question of whether\n'
+                 'this increase also bears substantive significance can only be answered\n'
+                 f'by comparing the absolute effect ({r(a["abs_effect"])}) to the original goal\n'
+                 'of the underlying intervention.\n')
+    elif detected:
+        p.append('\n\nThis means that the negative effect observed during the intervention\n'
+                 'period is statistically significant.\n'
+                 'If the experimenter had expected a positive effect, it is recommended\n'
+                 'to double-check whether anomalies in the control variables may have\n'
+                 'caused an overly optimistic expectation of what should have happened\n'
+                 'in the response variable in the absence of the intervention.\n')
+    elif positive:
+        p.append('\n\nThis means that, although the intervention appears to have caused a\n'
+                 'positive effect, this effect is not statistically significant when\n'
+                 'considering the entire post-intervention period as a whole. Individual\n'
+                 'days or shorter stretches within the intervention period may of course\n'
+                 'still have had a significant effect, as indicated whenever the lower\n'
+                 'limit of the impact time series (lower plot) was above zero.\n')
+    else:
+        p.append('This means that, although it may look as though the intervention has\n'
+                 'exerted a negative effect on the response variable when considering\n'
+                 'the intervention period as a whole, this effect is not statistically\n'
+                 'significant and so cannot be meaningfully interpreted.\n')
+    if not detected:
+        p.append('\n\nThe apparent effect could be the result of random fluctuations that\n'
+                 'are unrelated to the intervention. This is often the case when the\n'
+                 'intervention period is very long and includes much of the time when\n'
+                 'the effect has already worn off. It can also be the case when the\n'
+                 'intervention period is too short to distinguish the signal from the\n'
+                 'noise. Finally, failing to find a significant effect can happen when\n'
+                 'there are not enough control variables or when these variables do not\n'
+                 'correlate well with the response variable during the learning period.\n')
+    if p_value < alpha:
+        p.append('\n\nThe probability of obtaining this effect by chance is very small\n'
+                 f'(Bayesian one-sided tail-area probability p = {round(float(p_value), digits)}).\n'
+                 'This means the causal effect can be considered statistically\n'
+                 'significant.')
+    else:
+        p.append(f'\n\nThe probability of obtaining this effect by chance is p = {round(float(p_value) * 100, digits)}%.\n'
+                 'This means the effect may be spurious and would generally not be\n'
+                 'considered statistically significant.')
+    return ''.join(p)
 
 
 def summary(summary_data: pd.DataFrame, p_value: float, alpha: float = 0.05, output: str = 'summary',
