@@ -116,14 +116,33 @@ def test_rhat_across_chains_cfg3_shape():
     draws, stats = db.hmc_run(u, step0, 600, 300, 240, 15, 0.75, seed=3)       # [R, P, N*C]
     R, P, B = draws.shape
     d = draws.view(R, P, N, C).double()
-    # scale parameters and the realised regression weights mix well; compare on the two scales
-    half = R // 2
-    chains = torch.cat([d[:half], d[half:2 * half]], dim=3)                      # split chains: [half, P, N, 2C]
-    m = chains.mean(dim=0)
-    W = chains.var(dim=0, unbiased=True).mean(dim=2)
-    Bv = half * m.var(dim=2, unbiased=True)
-    rhat = torch.sqrt(((half - 1) / half * W + Bv / half) / W)                   # [P, N]
-    rh_scales = rhat[[0, 1, P - 1]]
+    def split_rhat(x):                                                           # x [R, ..., N, C] -> [..., N]
+        half = x.shape[0] // 2
+        ch = torch.cat([x[:half], x[half:2 * half]], dim=-1)                     # split chains: 2C per series
+        m = ch.mean(dim=0)
+        W = ch.var(dim=0, unbiased=True).mean(dim=-1)
+        Bv = half * m.var(dim=-1, unbiased=True)
+        return torch.sqrt(((half - 1) / half * W + Bv / half) / W)
+    d = draws.view(R, P, N, C).double()
+    rh_scales = split_rhat(d)[[0, 1, P - 1]]                                     # sigma_obs, sigma_level, sigma_drift
     assert float(stats[0].mean()) > 0.5
     assert float(rh_scales.median()) < 1.05, rh_scales.median()
     assert float((rh_scales < 1.2).double().mean()) > 0.9
+    # the regression block, where HMC actually struggles (horseshoe funnel): realised weights
+    # beta = wn * (lsn sqrt(lsv)) * (gsn sqrt(gsv) 0.1) and the log global / local scales, from the CONSTRAINED draws
+    theta = torch.stack([db.constrain(draws[r].contiguous()) for r in range(R)]).view(R, P, N, C).double()
+    gsv, gsn = theta[:, 2], theta[:, 3]
+    lsv, lsn, wn = theta[:, 4:4 + k], theta[:, 4 + k:4 + 2 * k], theta[:, 4 + 2 * k:4 + 3 * k]
+    tau = gsn * gsv.sqrt() * 0.1                                                 # [R, N, C]
+    lam = lsn * lsv.sqrt()                                                       # [R, k, N, C]
+    beta = wn * lam * tau[:, None]
+    rh_beta, rh_tau, rh_lam = split_rhat(beta), split_rhat(tau.log()), split_rhat(lam.log())
+    msg = (float(rh_beta.median()), float(rh_beta.max()), float(rh_tau.median()), float(rh_tau.max()),
+           float(rh_lam.median()), float(rh_lam.quantile(0.95)))
+    print('split R-hat (median, max): beta %.3f %.3f | log tau %.3f %.3f | log lambda (median, q95) %.3f %.3f' % msg)
+    # what users consume -- the realised weights -- must mix; the horseshoe's global scale sits at the neck of the
+    # funnel and mixes slowly under the reference's sampler settings (identity mass, L = 15, 300 warm-up steps: the
+    # same algorithm), so its gate only guards against divergence, the measured values are printed
+    assert float(rh_beta.median()) < 1.05 and float((rh_beta < 1.2).double().mean()) > 0.95, msg
+    assert float(rh_lam.median()) < 1.1 and float((rh_lam < 1.5).double().mean()) > 0.9, msg
+    assert float(rh_tau.median()) < 2.0, msg
