@@ -23,6 +23,13 @@ def timed(name, fn, bytes_moved=None, reps=3):
     print(json.dumps(rec), flush=True)
     return out
 B = N * D
+import ctypes
+from tfcausalimpact_b200 import _native as nt
+def opt(name, v): nt.check(nt.lib().ci_set_option(name, ctypes.c_long(v)), 'opt')
+if os.environ.get('AB'):
+    for v, tag in ((0, 'three kernels'), (1, 'fused')):
+        opt(b'filter_fused', v)
+        timed(f'ci_filter_predict [{tag}]', lambda: db.filter_predict(u), bytes_moved=2 * T * B * 4 + db.X.numel() * 4)
 pm, pv, fs = timed('ci_filter_predict (1M lanes x 365)', lambda: db.filter_predict(u), bytes_moved=2 * T * B * 4 + db.X.numel() * 4)
 sims_post, mean_post = timed('ci_forecast_sample (N x 1000 x 30)', lambda: db.forecast_sample(u, fs, niter, 3, mu_sig), bytes_moved=N * niter * Tf * 4)
 npre = min(N, 2000)   # pre-period sample tensor of 2000 series = 2.9 GB

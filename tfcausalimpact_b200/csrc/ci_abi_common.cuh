@@ -83,6 +83,8 @@ int launch_forecast_moments_big(const ci_layout* L, const float* fs, const float
 void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
                          const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t stream);
 
+extern int g_filter_fused;                      // ci_predict.cu tuning hook (ci_set_option)
+
 // ---- lane-cooperative evaluation for sub-wave batches, ci_eval_coop.cu -----------------------------
 bool coop_eligible(const ci_layout* L);         // layout + lane count served by the cooperative kernel
 size_t coop_tape_floats(const ci_layout* L);    // [warps][T][32], lanes padded to 8

@@ -146,10 +146,11 @@ CI_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-CI_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
+template <int ROUNDS>
+CI_HD u32x4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < ROUNDS; ++i) {
     uint32_t hi0, lo0, hi1, lo1;
     mulhilo(0xD2511F53u, c0, hi0, lo0);
     mulhilo(0xCD9E8D57u, c2, hi1, lo1);
@@ -159,6 +160,9 @@ CI_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint6
     k1 += 0xBB67AE85u;
   }
   return u32x4{c0, c1, c2, c3};
+}
+CI_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed) {
+  return philox4x32_r<10>(c0, c1, c2, c3, seed);
 }
 
 // (0,1) uniform with 24 random bits: ((x >> 8) + 0.5) * 2^-24 -- exact in fp32.
@@ -190,12 +194,15 @@ CI_HD f32x4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, 
   return f32x4{r0 * c0f, r0 * s0, r1 * c1f, r1 * s1};
 }
 
-// Same Philox stream, Box-Muller on the special-function unit (MUFU lg2 / sin / cos / sqrt, angle in
-// [-pi, pi)): for the posterior-predictive SAMPLERS only, whose contract is distributional (absolute error
-// of a draw ~1e-6); the fit drivers keep philox_normal4, which the oracle reproduces.
+// Philox4x32-7 (the smallest round count that passes BigCrush, Salmon et al. 2011, table 2) + Box-Muller on the
+// special-function unit (MUFU lg2 / sin / cos / sqrt, angle in [-pi, pi)): for the posterior-predictive SAMPLERS
+// only, whose contract is distributional (absolute error of a draw ~1e-6) and whose cost is dominated by the
+// generator (a 10-round call is ~100 of the ~170 instructions of a forecast step); the fit drivers keep the
+// 10-round philox_normal4, which the oracle reproduces bit for bit.
 CI_HD f32x4 philox_normal4_fast(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, uint64_t seed) {
 #if defined(__CUDA_ARCH__)
-  const f32x4 u = philox_uniform4(c0, c1, c2, tag, seed);
+  const u32x4 rr = philox4x32_r<7>(c0, c1, c2, tag, seed);
+  const f32x4 u = f32x4{u32_to_unit(rr.x), u32_to_unit(rr.y), u32_to_unit(rr.z), u32_to_unit(rr.w)};
   const float r0 = __fsqrt_rn(-2.0f * __logf(u.x)), r1 = __fsqrt_rn(-2.0f * __logf(u.z));
   const float two_pi = 6.283185307179586f;
   const float a0 = two_pi * (u.y - 0.5f), a1 = two_pi * (u.w - 0.5f);

@@ -552,6 +552,9 @@ int ci_set_option(const char* name, long value) {
     tpl = (int)value;
   } else if (!strcmp(name, "coop_max_lanes")) {
     max_lanes = value;
+  } else if (!strcmp(name, "filter_fused")) {
+    g_filter_fused = value != 0;
+
   } else {
     return fail(CI_ERR_INVALID_ARGUMENT, "unknown option %s", name);
   }

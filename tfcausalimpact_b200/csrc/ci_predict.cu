@@ -13,6 +13,7 @@
 // (y * sigma + mu, causalimpact/misc.py:75-77) when d_mu_sig is given.
 #include "ci_abi_common.cuh"
 #include "ci_kalman.cuh"
+#include "ci_xstage.cuh"
 
 namespace ci {
 
@@ -111,6 +112,140 @@ k_filter(int N, int G, int T, int r, const float* __restrict__ y, const float* _
   for (int i = 0; i < NP; ++i) fstate[(long)(S + NP + i) * B + b] = Lf[i];
 }
 
+// Fused forward filter (K6): ONE kernel per call.  A lane = one (series, posterior draw); the parameter
+// transform, the regression offsets and the filter run in the same thread, exactly as the forward half of the
+// evaluation kernel (ci_eval.cu): -beta lives in a shared-memory column, the (X, y) chunk of the warp's series
+// run is TMA-bulk-copied into shared memory behind a per-warp mbarrier while the previous chunk's steps run, the
+// state stays in registers.  Nothing but the outputs goes to HBM (the unfused path wrote and re-read a [T][B]
+// offset array and re-derived it in a separate LSU-bound kernel).  Padding lanes shadow the last lane.
+__host__ __device__ inline int filter_series_max(int G) {
+  const int a = (32 + G - 2) / G + 1;
+  return a < 32 ? a : 32;
+}
+// (The seasonal-effects frame of the evaluation kernel was measured here too: with its 8 x 8 covariance and the
+// per-step season dispatch the forward-only filter took 4.16 ms against 3.45 ms for 1M lanes x 365 -- not kept.)
+template <int S>
+__global__ void __launch_bounds__(32, 16)
+k_filter_fused(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* __restrict__ u,
+               float* __restrict__ pred_mean, float* __restrict__ pred_var, float* __restrict__ fstate) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NP = S * (S + 1) / 2;
+  const int N = L.N, G = L.G, T = L.T, k = L.k, r = L.r;
+  const long B = (long)N * G;
+  const long bw0 = (long)blockIdx.x * 32;
+  const bool valid = bw0 + threadIdx.x < B;
+  const long b = valid ? bw0 + threadIdx.x : B - 1;
+  const int n = (int)(b / G);
+  const int stride = (k + 1) * CI_TC;
+  float* sb = smem + threadIdx.x;                         // [k][32]: MINUS beta
+  const int smax = filter_series_max(G);
+  float* sx = smem + (long)k * 32;                        // [smax][stride]
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(sx + (long)smax * stride);
+  const int n_lo = (int)(bw0 / G);
+  const long b_last = (bw0 + 31 < B ? bw0 + 31 : B - 1);
+  const int ns = (int)(b_last / G) - n_lo + 1;
+  XStaged xs;
+  xs.lane_x = sx + (long)(n - n_lo) * stride;
+  xs.bar = smem_u32(wbase);
+  xs.parity = 0u;
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<uint64_t*>(wbase + 16) = reinterpret_cast<uint64_t>(XY + (long)n_lo * stride);
+    *reinterpret_cast<uint32_t*>(wbase + 24) = (uint32_t)ns * (uint32_t)stride * 4u;
+    *reinterpret_cast<uint32_t*>(wbase + 28) = smem_u32(sx);
+    *reinterpret_cast<uint64_t*>(wbase + 32) = (uint64_t)((long)N * stride) * 4u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs.bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) xs.issue(0);
+  const float* sc = sconst + n;
+  const LaneScalars ls = params_forward_lane(u + b, B, k, L.S, sc, N, sb, 32, -1.0f);
+  const float R = ls.R, ql = ls.ql, qd = ls.qd;
+  const float mean = sc[SC_MEAN * N];
+  KState<S> ks;
+  kf_init<S>(ks, sc[SC_M0 * N], sc[SC_P0 * N]);
+  const int nchunk = (T + CI_TC - 1) / CI_TC;
+  int phase = 0;
+  float* pmp = pred_mean + b;
+  float* pvp = pred_var + b;
+  for (int tc = 0; tc < nchunk; ++tc) {
+    xs.acquire();
+    const float* __restrict__ xp = xs.lane_x;
+    const float4 yv = *reinterpret_cast<const float4*>(xp + k * CI_TC);          // row k: centred series
+    pf2 a01 = mk2(0.f, 0.f), a23 = mk2(0.f, 0.f), c01 = mk2(0.f, 0.f), c23 = mk2(0.f, 0.f);
+    int j = 0;
+    for (; j + 2 <= k; j += 2) {
+      const float n0 = sb[j * 32], n1 = sb[(j + 1) * 32];
+      const float4 x0 = *reinterpret_cast<const float4*>(xp + j * CI_TC);
+      const float4 x1 = *reinterpret_cast<const float4*>(xp + (j + 1) * CI_TC);
+      a01 = ffma2(mk2(n0, n0), mk2(x0.x, x0.y), a01);
+      a23 = ffma2(mk2(n0, n0), mk2(x0.z, x0.w), a23);
+      c01 = ffma2(mk2(n1, n1), mk2(x1.x, x1.y), c01);
+      c23 = ffma2(mk2(n1, n1), mk2(x1.z, x1.w), c23);
+    }
+    if (j < k) {
+      const float n0 = sb[j * 32];
+      const float4 x0 = *reinterpret_cast<const float4*>(xp + j * CI_TC);
+      a01 = ffma2(mk2(n0, n0), mk2(x0.x, x0.y), a01);
+      a23 = ffma2(mk2(n0, n0), mk2(x0.z, x0.w), a23);
+    }
+    a01 = fadd2(a01, c01);
+    a23 = fadd2(a23, c23);
+    xs.release(tc + 1 < nchunk ? tc + 1 : -1);
+    const float acc[CI_TC] = {a01.x, a01.y, a23.x, a23.y};                       // -X_t . beta
+    const float yc[CI_TC] = {yv.x, yv.y, yv.z, yv.w};
+    const int nstep = (T - tc * CI_TC) < CI_TC ? (T - tc * CI_TC) : CI_TC;
+#pragma unroll
+    for (int i = 0; i < CI_TC; ++i) {
+      if (i < nstep) {
+        const float rr = yc[i] + acc[i];                                         // NaN = missing step
+        float hm = ks.m[0], s = ks.P[sym<S>(0, 0)] + R;
+        if (S > 1) {
+          hm += ks.m[1];
+          s += 2.f * ks.P[sym<S>(0, 1)] + ks.P[sym<S>(1, 1)];
+        }
+        if (valid) {
+          *pmp = hm + mean - acc[i];
+          *pvp = s;
+        }
+        pmp += B;
+        pvp += B;
+        if (rr == rr) {
+          float g[S], s2, v, is;
+          kf_update<S>(ks, rr, R, g, s2, v, is);
+        }
+        const bool change = (phase == r - 1);
+        kf_predict<S>(ks, ql, qd, change);
+        phase = change ? 0 : phase + 1;
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int i = 0; i < S; ++i) fstate[(long)i * B + b] = ks.m[i];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) fstate[(long)(S + i) * B + b] = ks.P[i];
+  // guarded Cholesky (a non-positive pivot zeroes its column), row-major packed lower factor
+  float Lf[NP];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      float a = ks.P[sym<S>(i, j)];
+#pragma unroll
+      for (int q = 0; q < j; ++q) a = fmaf(-Lf[i * (i + 1) / 2 + q], Lf[j * (j + 1) / 2 + q], a);
+      if (i == j) {
+        Lf[i * (i + 1) / 2 + j] = a > 0.f ? sqrtf(a) : 0.f;
+      } else {
+        const float dj = Lf[j * (j + 1) / 2 + j];
+        Lf[i * (i + 1) / 2 + j] = dj > 0.f ? a / dj : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) fstate[(long)(S + NP + i) * B + b] = Lf[i];
+}
+
 __device__ __forceinline__ uint32_t pick_draw(uint32_t sample_id, uint32_t stream, int G, uint64_t seed) {
   const float un = philox_uniform4(sample_id, 0u, stream, TAG_PICK, seed).x;
   const int j = (int)(un * (float)G);
@@ -156,6 +291,9 @@ k_onestep_sample(int N, int G, int T, int nsamp, uint64_t seed, const float* __r
   }
 }
 
+// (Staging the [32][G] blocks of pred_mean / sqrt(pred_var) of the series in shared memory was measured: 5.50 ms against
+// 4.15 ms for 2000 series x 1000 samples x 365 steps -- a 128-sample CTA re-uses a staged value only 1.3 times (G = 100
+// draws), so the staging loop costs more than the L1-served gathers it replaces.  Not kept.)
 // out[n][t] = mean over the G draws of a[t][n*G + j], unstandardised.
 __global__ void k_mean_over_draws(int N, int G, int W, const float* __restrict__ a,
                                   const float* __restrict__ mu_sig, float* __restrict__ out) {
@@ -240,23 +378,34 @@ k_forecast_sample(int N, int G, int T, int Tf, int r, int nsamp, uint64_t seed,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t0 = 0; t0 < Tf; t0 += 32) {
     const int tn = min(32, Tf - t0);
-    for (int q = 0; q < tn; ++q) {
-      const int t = t0 + q;
-      const f32x4 e = philox_normal4_fast((uint32_t)si, (uint32_t)t, 0u, TAG_FORECAST, seed);
-      const float yv = x[0] + (S > 1 ? x[1] : 0.f) + off[(long)t * B + b] + so * e.x;
-      tile[threadIdx.x][q] = fmaf(yv, sg, mu);
-      x[0] = fmaf(sl, e.y, x[0]);
-      const bool change = (phase == r - 1);
-      if (S > 1 && change) {
-        float zs = 0.f;
+    for (int q0 = 0; q0 < tn; q0 += 4) {
+      // 12 normals per 4 steps (observation, level and drift noise of each) from THREE generator calls
+      const uint32_t grp = (uint32_t)((t0 + q0) >> 2) * 3u;
+      const f32x4 na = philox_normal4_fast((uint32_t)si, grp, 0u, TAG_FORECAST, seed);
+      const f32x4 nb = philox_normal4_fast((uint32_t)si, grp + 1u, 0u, TAG_FORECAST, seed);
+      const f32x4 nc = philox_normal4_fast((uint32_t)si, grp + 2u, 0u, TAG_FORECAST, seed);
+      const float nz[12] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w};
 #pragma unroll
-        for (int a = 1; a < S; ++a) zs += x[a];
-        const float xi = sdr * e.z;
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const int q = q0 + e4;
+        if (q < tn) {
+          const int t = t0 + q;
+          const float yv = x[0] + (S > 1 ? x[1] : 0.f) + off[(long)t * B + b] + so * nz[3 * e4];
+          tile[threadIdx.x][q] = fmaf(yv, sg, mu);
+          x[0] = fmaf(sl, nz[3 * e4 + 1], x[0]);
+          const bool change = (phase == r - 1);
+          if (S > 1 && change) {
+            float zs = 0.f;
 #pragma unroll
-        for (int a = 1; a < S - 1; ++a) x[a] = x[a + 1] + xi;
-        x[S - 1] = -zs + xi;
+            for (int a = 1; a < S; ++a) zs += x[a];
+            const float xi = sdr * nz[3 * e4 + 2];
+#pragma unroll
+            for (int a = 1; a < S - 1; ++a) x[a] = x[a + 1] + xi;
+            x[S - 1] = -zs + xi;
+          }
+          phase = change ? 0 : phase + 1;
+        }
       }
-      phase = change ? 0 : phase + 1;
     }
     __syncthreads();
     for (int row = warp; row < 128; row += 4) {
@@ -274,6 +423,25 @@ static void launch_filter(const ci_layout* L, const ci_data* D, const PredWs& ws
   k_filter<S><<<(unsigned)((B + 63) / 64), 64, 0, st>>>(L->N, L->G, L->T, L->r, D->d_y, D->d_sconst, ws.scal, ws.off,
                                                          pm, pv, fs);
 }
+static size_t filter_fused_smem(const ci_layout* L) {
+  return ((size_t)L->k * 32 + (size_t)filter_series_max(L->G) * (L->k + 1) * CI_TC) * 4 + 48;
+}
+template <int S>
+static int launch_filter_fused(const ci_layout* L, const ci_data* D, const float* d_u, float* pm, float* pv, float* fs,
+                               cudaStream_t st) {
+  const long B = (long)L->N * L->G;
+  const size_t smem = filter_fused_smem(L);
+  auto kern = k_filter_fused<S>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<(unsigned)((B + 31) / 32), 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, pm, pv, fs);
+  return CI_OK;
+}
 template <int S>
 static void launch_forecast(const ci_layout* L, const FcWs& ws, const float* fs, const float* mu_sig, int nsamp,
                             uint64_t seed, float* sims, cudaStream_t st) {
@@ -283,6 +451,8 @@ static void launch_forecast(const ci_layout* L, const FcWs& ws, const float* fs,
     k_forecast_sample<S><<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(L->N, L->G, L->T, L->Tf, L->r, nsamp, seed,
                                                                          fs, ws.scal, ws.off, mu_sig, sims);
 }
+
+int g_filter_fused = 1;   // ci_set_option("filter_fused", 0 / 1): three kernels / one fused kernel
 
 }  // namespace ci
 
@@ -311,6 +481,13 @@ int ci_filter_predict(const ci_layout* L, const ci_data* D, const float* d_u, fl
   pred_ws_floats(L, &ws, &c);
   if (!ci_reg_path(L)) {
     if (int e = launch_filter_big(L, D, d_u, d_pred_mean, d_pred_var, d_fstate, st)) return e;
+    CI_CHECK_LAUNCH();
+    return CI_OK;
+  }
+  if (g_filter_fused && filter_fused_smem(L) <= 100 * 1024) {
+    int rc = CI_OK;
+    CI_DISPATCH_S(L->S, (rc = launch_filter_fused<S_>(L, D, d_u, d_pred_mean, d_pred_var, d_fstate, st)));
+    if (rc) return rc;
     CI_CHECK_LAUNCH();
     return CI_OK;
   }
