@@ -83,6 +83,12 @@ int launch_forecast_moments_big(const ci_layout* L, const float* fs, const float
 void launch_forecast_big(const ci_layout* L, const float* fs, const float* scal, const float* off, float* pm,
                          const float* mu_sig, int nsamp, uint64_t seed, float* sims, cudaStream_t stream);
 
+// ---- few lanes, large latent: 4 warps per lane, covariance in registers, ci_eval_rw.cu ----------------
+extern int g_eval_rw, g_rw_warps;
+bool rw_eligible(const ci_layout* L);
+int launch_eval_rw(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad, float* tape,
+                   float* rscr, cudaStream_t stream);
+
 extern int g_filter_fused;                      // ci_predict.cu tuning hook (ci_set_option)
 
 // ---- lane-cooperative evaluation for sub-wave batches, ci_eval_coop.cu -----------------------------

@@ -1172,6 +1172,8 @@ size_t big_fstate_floats(const ci_layout* L) {
   return D + 2 * D * D;
 }
 
+int g_eval_rw = 1;   // ci_set_option("eval_rw", 0 / 1): register-resident 4-warp kernel (ci_eval_rw.cu) on / off
+
 template <class K>
 static int big_attr(K kern, size_t smem) {
   if (smem > 48 * 1024) {
@@ -1184,6 +1186,10 @@ static int big_attr(K kern, size_t smem) {
 int launch_eval_big(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                     float* tape, cudaStream_t st) {
   if (!big_supported(L)) return fail(CI_ERR_UNSUPPORTED, "nseasons=%d exceeds the shared-memory latent budget", L->S);
+  if (g_eval_rw && rw_eligible(L)) {
+    const long B = (long)L->N * L->G;
+    return launch_eval_rw(L, D, d_u, d_logp, d_grad, tape, tape + (size_t)B * L->T * (big_D(*L) + 1), st);
+  }
   if (big_use_cta(L)) {
 #ifndef CI_CTA_RG
 #define CI_CTA_RG 8

@@ -552,6 +552,11 @@ int ci_set_option(const char* name, long value) {
     tpl = (int)value;
   } else if (!strcmp(name, "coop_max_lanes")) {
     max_lanes = value;
+  } else if (!strcmp(name, "eval_rw")) {
+    g_eval_rw = value != 0;
+  } else if (!strcmp(name, "eval_rw_warps")) {
+    CI_CHECK_ARG(value == 4 || value == 8, "eval_rw_warps must be 4 or 8");
+    g_rw_warps = (int)value;
   } else if (!strcmp(name, "filter_fused")) {
     g_filter_fused = value != 0;
 
