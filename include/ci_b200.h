@@ -118,6 +118,7 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
  *   "coop_max_lanes"         largest N * G served by it (-1 = default: the measured crossover)
  *   "eval_rw"                1 (default) few-lane / large-latent evaluations run on the register-resident 4-warp kernel
  *   "filter_fused"           1 (default) ci_filter_predict runs as one fused kernel, 0 = the three-kernel path
+ *   "onestep_tiled"          1 (default) ci_onestep_sample stages each series' predictive moments in shared memory
  * The lane-cooperative kernel (csrc/ci_eval_coop.cu) serves default-model layouts with 2 <= nseasons <= 7,
  * season_duration 1, whose lanes cannot fill the GPU at one thread per lane. */
 int ci_set_option(const char* name, long value);

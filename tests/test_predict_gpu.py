@@ -105,6 +105,44 @@ def test_onestep_sampler_moments_and_mean():
     assert float((sims2 - sims).abs().max()) > 0.0
 
 
+@pytest.mark.parametrize('tiled', [1, 0])
+@pytest.mark.parametrize('N,G,T,nsamp', [(3, 5, 37, 4099), (2, 7, 31, 33), (1, 100, 365, 1000), (5, 1, 70, 258)])
+def test_onestep_sampler_edge_shapes(tiled, N, G, T, nsamp):
+    """Both sampler kernels (tiled lane-per-step with aligned runs / sample-per-thread gather) on ragged shapes:
+    several slabs per series, a partial last quad, T below one block, one draw; every element written, per-step
+    moments of the mixture, no correlation between consecutive steps or consecutive samples."""
+    import ctypes
+    from tfcausalimpact_b200 import _native as nt
+    Tf, k, S = 5, 1, 4
+    L, prob, db = _setup(N, T, Tf, k, S, 1, 29, 0.0)
+    u = _draws(L, N * G, 5)
+    pm, pv, fs = db.filter_predict(torch.as_tensor(u).cuda())
+    nt.check(nt.lib().ci_set_option(b'onestep_tiled', ctypes.c_long(tiled)), 'opt')
+    try:
+        # NaN-prefill the block the caching allocator hands out next: an element the kernel skips stays NaN
+        x = torch.full((N, nsamp, T), float('nan'), device='cuda')
+        del x
+        sims, mean = db.onestep_sample(pm, pv, nsamp, seed=11)
+    finally:
+        nt.check(nt.lib().ci_set_option(b'onestep_tiled', ctypes.c_long(1)), 'opt')
+    s = sims.cpu().numpy().astype(np.float64)
+    assert s.shape == (N, nsamp, T) and np.all(np.isfinite(s))
+    pmn = pm.cpu().numpy().reshape(T, N, G).astype(np.float64)
+    pvn = pv.cpu().numpy().reshape(T, N, G).astype(np.float64)
+    mix_mean = pmn.mean(axis=2).T
+    np.testing.assert_allclose(mean.cpu().numpy(), mix_mean, rtol=1e-5, atol=1e-6)
+    mix_var = (pvn + pmn ** 2).mean(axis=2).T - mix_mean ** 2
+    assert np.all(np.abs(s.mean(axis=1) - mix_mean) < 5 * np.sqrt(mix_var / nsamp))
+    if nsamp >= 1000:
+        assert np.all(np.abs(s.var(axis=1) / mix_var - 1.0) < 0.3)
+    if G == 1:
+        # one draw: y_t independent over t and over samples -> standardised residuals are white noise
+        z = (s - mix_mean[:, None, :]) / np.sqrt(mix_var)[:, None, :]
+        n_el = z[:, :, 1:].size
+        assert abs((z[:, :, 1:] * z[:, :, :-1]).mean()) < 5 / np.sqrt(n_el)
+        assert abs((z[:, 1:, :] * z[:, :-1, :]).mean()) < 5 / np.sqrt(n_el)
+
+
 def test_forecast_sampler_single_draw_covariance():
     """With a single posterior draw the samples are one Gaussian process: check the variance of the
     path SUM (needs the cross-time covariance, i.e. joint trajectories) against a dense oracle."""

@@ -89,6 +89,7 @@ bool rw_eligible(const ci_layout* L);
 int launch_eval_rw(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad, float* tape,
                    float* rscr, cudaStream_t stream);
 
+extern int g_onestep_tiled;                    // ci_predict.cu tuning hook (ci_set_option)
 extern int g_filter_fused;                      // ci_predict.cu tuning hook (ci_set_option)
 
 // ---- lane-cooperative evaluation for sub-wave batches, ci_eval_coop.cu -----------------------------

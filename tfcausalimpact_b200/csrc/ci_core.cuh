@@ -202,10 +202,17 @@ CI_HD f32x4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, 
 CI_HD f32x4 philox_normal4_fast(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag, uint64_t seed) {
 #if defined(__CUDA_ARCH__)
   const u32x4 rr = philox4x32_r<7>(c0, c1, c2, tag, seed);
-  const f32x4 u = f32x4{u32_to_unit(rr.x), u32_to_unit(rr.y), u32_to_unit(rr.z), u32_to_unit(rr.w)};
-  const float r0 = __fsqrt_rn(-2.0f * __logf(u.x)), r1 = __fsqrt_rn(-2.0f * __logf(u.z));
-  const float two_pi = 6.283185307179586f;
-  const float a0 = two_pi * (u.y - 0.5f), a1 = two_pi * (u.w - 0.5f);
+  // radius: u = ((x >> 8) + 0.5) 2^-24 in (0, 1), never denormal -> lg2.approx.ftz; sqrt(-2 ln u) = sqrt(-2 ln2 lg2 u)
+  // angle:  2 pi (u - 0.5) in [-pi, pi) straight from the integer: one conversion + one FMA
+  const float ux = fmaf((float)(rr.x >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+  const float uz = fmaf((float)(rr.z >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+  const float a0 = fmaf((float)(rr.y >> 8), 3.7450702829239664e-07f, -3.1415924662916617f);
+  const float a1 = fmaf((float)(rr.w >> 8), 3.7450702829239664e-07f, -3.1415924662916617f);
+  float l0, l1, r0, r1;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(ux));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(uz));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-1.3862943611198906f * l0));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-1.3862943611198906f * l1));
   return f32x4{r0 * __cosf(a0), r0 * __sinf(a0), r1 * __cosf(a1), r1 * __sinf(a1)};
 #else
   return philox_normal4(c0, c1, c2, tag, seed);

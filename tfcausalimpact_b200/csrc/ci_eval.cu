@@ -559,6 +559,8 @@ int ci_set_option(const char* name, long value) {
     g_rw_warps = (int)value;
   } else if (!strcmp(name, "filter_fused")) {
     g_filter_fused = value != 0;
+  } else if (!strcmp(name, "onestep_tiled")) {
+    g_onestep_tiled = value != 0;
 
   } else {
     return fail(CI_ERR_INVALID_ARGUMENT, "unknown option %s", name);

@@ -291,9 +291,124 @@ k_onestep_sample(int N, int G, int T, int nsamp, uint64_t seed, const float* __r
   }
 }
 
-// (Staging the [32][G] blocks of pred_mean / sqrt(pred_var) of the series in shared memory was measured: 5.50 ms against
-// 4.15 ms for 2000 series x 1000 samples x 365 steps -- a 128-sample CTA re-uses a staged value only 1.3 times (G = 100
-// draws), so the staging loop costs more than the L1-served gathers it replaces.  Not kept.)
+// pre_sims[n][i][t], tiled version (G <= ONESTEP_TILED_MAX_G draws).  One CTA = one series x a slab of samples.  The
+// (mean, sd) of ALL G draws of the series are staged per block of 32 steps in shared memory, already unstandardised
+// (a staged value serves slab / G samples); a warp walks the slab four samples at a time with LANE = TIME STEP: one
+// Philox call = four normals, one per sample of the quad; the picked draw is warp-uniform (conflict-free shared-memory
+// reads at odd row pitch) and every store instruction writes one 128-byte run of a [nsamp][T] row.
+//   * ALIGNED RUNS.  Rows are T floats long, so a run that starts at a multiple of 32 steps is not 128-byte aligned
+//     in memory and every store leaves two partially written sectors behind: measured 2.79 ms (T = 365) against
+//     1.37 ms (T = 384) for 2000 series x 1000 samples.  Each sample therefore shifts its runs by a_i = (-row start)
+//     mod 32: iteration m of the CTA covers t in [a_i + 32 (m - 1), a_i + 32 m), i.e. whole 128-byte lines of the
+//     output; the staged window holds the two blocks of 32 steps such a run can touch.
+//   * The raw (mean, variance) block of the NEXT 32 steps lands in a second pair of shared-memory arrays by cp.async
+//     while the current runs are sampled (the moments are not L2-resident: 584 MB for 2000 series).
+// (A first staged variant with 128-sample CTAs re-used a staged value only 1.3 times and lost to the L1-served gathers
+// of k_onestep_sample: 5.50 against 4.15 ms for 2000 series x 1000 samples x 365 steps.)
+#define ONESTEP_TILED_MAX_G 128
+#define ONESTEP_NT 512          // threads per CTA of the tiled sampler
+__global__ void __launch_bounds__(ONESTEP_NT)
+k_onestep_sample_tiled(int N, int G, int T, int nsamp, int slab, uint64_t seed, const float* __restrict__ pm,
+                       const float* __restrict__ pv, const float* __restrict__ mu_sig, float* __restrict__ sims,
+                       float* __restrict__ pre_mean) {
+  extern __shared__ __align__(16) float smem[];
+  const int GP = G | 1;
+  float2* sms = reinterpret_cast<float2*>(smem);                 // [64][GP] (mean, sd) of step t at row t & 63
+  float* raw = smem + 128 * GP;                                  // [2][32][G] raw mean / variance of the next block
+  unsigned short* sdraw = reinterpret_cast<unsigned short*>(raw + 64 * G);   // [slab] picked draw | run shift << 8
+  const int n = blockIdx.x;
+  const int i_lo = blockIdx.y * slab;
+  const int nloc = min(slab, nsamp - i_lo);
+  const long B = (long)N * G;
+  const float mu = mu_sig ? mu_sig[n] : 0.f, sg = mu_sig ? mu_sig[N + n] : 1.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* pmn = pm + (long)n * G;
+  const float* pvn = pv + (long)n * G;
+  const uint32_t raw_u32 = smem_u32(raw);
+  auto fetch = [&](int t0) {                                     // raw block of the 32 steps starting at t0 (may be empty)
+    const int tn = min(32, T - t0);
+    for (int tt = warp; tt < tn; tt += ONESTEP_NT / 32) {
+      const long o = (long)(t0 + tt) * B;
+      for (int j = lane; j < G; j += 32) {
+        const uint32_t d = raw_u32 + (uint32_t)(tt * G + j) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(pmn + o + j) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + (uint32_t)(32 * G) * 4u), "l"(pvn + o + j) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0);
+  const long row0 = (long)n * nsamp + i_lo;                      // first output row of the slab
+  for (int i = threadIdx.x; i < slab; i += ONESTEP_NT) {
+    unsigned v = 0u;
+    if (i < nloc) {
+      const unsigned shift = (unsigned)(32 - (int)(((row0 + i) * T) & 31)) & 31u;
+      v = pick_draw((uint32_t)(row0 + i), 0u, G, seed) | (shift << 8);
+    }
+    sdraw[i] = (unsigned short)v;
+  }
+  float* out0 = sims + row0 * T;
+  const uint32_t sid0 = (uint32_t)row0;
+  const uint32_t sms_u32 = smem_u32(sms);
+  const int nfull = nloc & ~3;
+  const size_t TQ = (size_t)T * (ONESTEP_NT / 8);
+  const int niter = (T - 1) / 32 + 2;                            // runs of a sample: a partial head, whole lines, a tail
+  for (int m = 0; m < niter; ++m) {
+    const int tb = 32 * m;                                       // block of steps staged in this iteration
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // raw block landed; the previous iteration is done
+    if (tb < T) {
+      const int tn = min(32, T - tb);
+      for (int tt = warp; tt < tn; tt += ONESTEP_NT / 32) {
+        float2* dst = sms + ((tb + tt) & 63) * GP;
+        float acc = 0.f;
+        for (int j = lane; j < G; j += 32) {
+          const float mj = raw[tt * G + j];
+          acc += mj;
+          dst[j] = make_float2(fmaf(mj, sg, mu), sqrtf(raw[32 * G + tt * G + j]) * sg);
+        }
+        if (pre_mean && blockIdx.y == 0) {                       // mixture mean over the draws (one_step_dist.mean())
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == 0) pre_mean[(long)n * T + tb + tt] = fmaf(acc / (float)G, sg, mu);
+        }
+      }
+    }
+    __syncthreads();
+    if (tb + 32 < T) fetch(tb + 32);
+    const int tl = tb - 32 + lane;                               // + shift = this lane's step
+    auto emit = [&](unsigned e16, float z, float* prow) {
+      const int t = tl + (int)(e16 >> 8);
+      if ((unsigned)t < (unsigned)T) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(v.x), "=f"(v.y)
+                     : "r"(sms_u32 + (uint32_t)((t & 63) * GP + (int)(e16 & 0xffu)) * 8u));
+        prow[t] = fmaf(v.y, z, v.x);
+      }
+    };
+    float* p0 = out0 + (size_t)(warp * 4) * T;
+    int q = warp * 4;
+    for (; q < nfull; q += ONESTEP_NT / 8) {
+      // counter = (first sample of the quad, iteration, lane): four normals, one per sample of the quad
+      const f32x4 z = philox_normal4_fast(sid0 + (uint32_t)q, (uint32_t)(tb + lane), 1u, TAG_ONESTEP, seed);
+      const uint2 jj = *reinterpret_cast<const uint2*>(sdraw + q);
+      emit(jj.x & 0xffffu, z.x, p0);
+      emit(jj.x >> 16, z.y, p0 + T);
+      emit(jj.y & 0xffffu, z.z, p0 + 2 * (size_t)T);
+      emit(jj.y >> 16, z.w, p0 + 3 * (size_t)T);
+      p0 += TQ;
+    }
+    if (q < nloc) {                                              // the slab's last, partial quad
+      const f32x4 z = philox_normal4_fast(sid0 + (uint32_t)q, (uint32_t)(tb + lane), 1u, TAG_ONESTEP, seed);
+      const uint2 jj = *reinterpret_cast<const uint2*>(sdraw + q);
+      emit(jj.x & 0xffffu, z.x, p0);
+      if (q + 1 < nloc) emit(jj.x >> 16, z.y, p0 + T);
+      if (q + 2 < nloc) emit(jj.y & 0xffffu, z.z, p0 + 2 * (size_t)T);
+    }
+  }
+}
+
 // out[n][t] = mean over the G draws of a[t][n*G + j], unstandardised.
 __global__ void k_mean_over_draws(int N, int G, int W, const float* __restrict__ a,
                                   const float* __restrict__ mu_sig, float* __restrict__ out) {
@@ -453,6 +568,7 @@ static void launch_forecast(const ci_layout* L, const FcWs& ws, const float* fs,
 }
 
 int g_filter_fused = 1;   // ci_set_option("filter_fused", 0 / 1): three kernels / one fused kernel
+int g_onestep_tiled = 1;  // ci_set_option("onestep_tiled", 0 / 1): sample-per-thread gather kernel / tiled lane-per-step kernel
 
 }  // namespace ci
 
@@ -505,8 +621,27 @@ int ci_onestep_sample(const ci_layout* L, const float* d_pred_mean, const float*
   CI_CHECK_ARG(nsamp >= 0 && (nsamp == 0 || d_pre_sims), "d_pre_sims is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (nsamp > 0) {
-    k_onestep_sample<<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(L->N, L->G, L->T, nsamp, seed, d_pred_mean,
-                                                                      d_pred_var, d_mu_sig, d_pre_sims);
+    if (g_onestep_tiled && L->G <= ONESTEP_TILED_MAX_G && L->N <= 65535 * 16) {
+      // slab of samples per CTA: a multiple of 4, at most 2048, small enough that the grid covers ~4 CTAs per SM
+      int nsl = (int)((4L * 148 + L->N - 1) / L->N);
+      if (nsl < (nsamp + 2047) / 2048) nsl = (nsamp + 2047) / 2048;
+      int slab = ((nsamp + nsl - 1) / nsl + 3) / 4 * 4;
+      if (slab < 32) slab = 32;
+      nsl = (nsamp + slab - 1) / slab;
+      const size_t smem = ((size_t)128 * (L->G | 1) + (size_t)64 * L->G) * 4 + (size_t)slab * 2 + 16;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_onestep_sample_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (e != cudaSuccess) return fail(CI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+      }
+      k_onestep_sample_tiled<<<dim3(L->N, nsl), ONESTEP_NT, smem, st>>>(L->N, L->G, L->T, nsamp, slab, seed, d_pred_mean,
+                                                                 d_pred_var, d_mu_sig, d_pre_sims, d_pre_mean);
+      d_pre_mean = nullptr;                    // written by the sampler's staging pass
+    } else {
+      k_onestep_sample<<<dim3((nsamp + 127) / 128, L->N), 128, 0, st>>>(L->N, L->G, L->T, nsamp, seed, d_pred_mean,
+                                                                        d_pred_var, d_mu_sig, d_pre_sims);
+    }
   }
   if (d_pre_mean) {
     const long total = (long)L->N * L->T;
