@@ -116,6 +116,7 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
 /* Tuning hook (process-wide, not part of the reference-facing contract; used by bench / A-B scripts):
  *   "coop_threads_per_lane"  -1 (default: chosen by lane count), 8, 4, or 0 = never use the lane-cooperative kernel
  *   "coop_max_lanes"         largest N * G served by it (-1 = default: the measured crossover)
+ *   "coop_mma"               1 (default) regression passes of the lane-cooperative kernel on the tensor cores (3xTF32), 0 = FFMA2
  *   "eval_rw"                1 (default) few-lane / large-latent evaluations run on the register-resident 4-warp kernel
  *   "filter_fused"           1 (default) ci_filter_predict runs as one fused kernel, 0 = the three-kernel path
  *   "onestep_tiled"          1 (default) ci_onestep_sample stages each series' predictive moments in shared memory

@@ -49,12 +49,13 @@ for N in [int(x) for x in os.environ.get('AB_SERIES', '16,125,625,1250,2500,5000
     db = DeviceBatch(y, X, Tf=Tf, nseasons=S)
     u = torch.randn(db.P, N * G, device='cuda') * 0.3
     row = {'series': N, 'chains': G, 'lanes': N * G, 'k': k}
-    for tpl in (0, 8, 4):
+    for tpl, mma in ((0, 1), (8, 1), (4, 0), (4, 1)):
         if tpl == 8 and N * G > 40000:
             continue
         opt(b'coop_threads_per_lane', tpl)
         opt(b'coop_max_lanes', 1 << 30)
-        tag = f'tpl{tpl}'
+        opt(b'coop_mma', mma)
+        tag = f'tpl{tpl}' + ('_ffma' if tpl == 4 and not mma else '')
         row[f'eval_ms_{tag}'] = round(time_eval(db, u), 4)
         if os.environ.get('AB_HMC', '1') == '1':
             row[f'hmc_ms_{tag}'] = round(time_hmc(db, u), 3)

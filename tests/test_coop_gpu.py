@@ -13,17 +13,18 @@ from helpers import O, synth_problem
 pytestmark = pytest.mark.gpu
 
 
-def _set(tpl, max_lanes=-1):
+def _set(tpl, max_lanes=-1, mma=1):
     from tfcausalimpact_b200 import _native as nt
     lib = nt.lib()
     nt.check(lib.ci_set_option(b'coop_threads_per_lane', ctypes.c_long(tpl)), 'ci_set_option')
     nt.check(lib.ci_set_option(b'coop_max_lanes', ctypes.c_long(max_lanes)), 'ci_set_option')
+    nt.check(lib.ci_set_option(b'coop_mma', ctypes.c_long(mma)), 'ci_set_option')
 
 
 @pytest.fixture(autouse=True)
 def _restore_default():
     yield
-    _set(-1, -1)
+    _set(-1, -1, 1)
 
 
 COOP_CASES = [
@@ -41,6 +42,11 @@ COOP_CASES = [
     (6, 8, 45, 0.3, 5, 4),
     (7, 50, 5, 0.0, 3, 8),       # T < a season cycle / the tape prefetch distance
     (7, 4, 9, 0.0, 1, 1),        # a single lane
+    # 8 / 16 chains per series: at 4 sub-threads the regression passes run on the tensor cores (3xTF32)
+    (7, 64, 33, 0.1, 2, 8),      # widest regression, odd number of 4-step chunks (ragged last 8-step group)
+    (7, 1, 30, 0.0, 2, 16),      # one covariate, two warps per series
+    (5, 3, 41, 0.0, 3, 8),
+    (2, 9, 9, 0.0, 1, 8),
 ]
 
 
@@ -73,6 +79,31 @@ def test_coop_logp_grad_matches_oracle(tpl, S, k, T, nan_frac, N, G):
     lp1, g1 = db.logp_grad(ud)
     np.testing.assert_allclose(lp, lp1.cpu().numpy(), rtol=2e-5, atol=2e-4)
     assert np.all(np.abs(g - g1.cpu().numpy()) <= 2e-4 * np.abs(go) + 4e-5 * gmax)
+
+
+@pytest.mark.parametrize('S,k,T,nan_frac,N,G', [c for c in COOP_CASES if c[5] % 8 == 0])
+def test_coop_tensor_core_passes_match_ffma_passes(S, k, T, nan_frac, N, G):
+    """The 3xTF32 tensor-core regression passes against the FFMA2 passes of the same kernel: same inputs, the two
+    differ only in the summation order / the dropped lo*lo term of the split (2^-22 relative)."""
+    from tfcausalimpact_b200.engine import DeviceBatch
+    Tf = 6
+    L = O.Layout(T, Tf, k, S, 1)
+    y, _, X = synth_problem(N, T, Tf, k, S, 1, seed=S * 100 + k + T, nan_frac=nan_frac)
+    db = DeviceBatch(y, X if k > 0 else None, Tf=Tf, nseasons=S)
+    rng = np.random.default_rng(3)
+    u = (rng.normal(size=(L.P, N * G)) * 0.7).astype(np.float32)
+    u[0] -= 1.0
+    u[1] -= 2.0
+    ud = torch.as_tensor(u).cuda()
+    out = {}
+    for mma in (1, 0):
+        _set(4, -1, mma)
+        lp, g = db.logp_grad(ud)
+        out[mma] = (lp.cpu().numpy().astype(np.float64), g.cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-5, atol=2e-4)
+    gmax = np.abs(out[0][1]).max(axis=0, keepdims=True)
+    assert np.all(np.abs(out[1][1] - out[0][1]) <= 5e-5 * np.abs(out[0][1]) + 2e-5 * gmax)
+    assert np.abs(out[1][1] - out[0][1]).max() > 0.0      # the two paths really are different code
 
 
 @pytest.mark.parametrize('tpl', [8, 4])

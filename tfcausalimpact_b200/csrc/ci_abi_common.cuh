@@ -95,6 +95,7 @@ extern int g_filter_fused;                      // ci_predict.cu tuning hook (ci
 // ---- lane-cooperative evaluation for sub-wave batches, ci_eval_coop.cu -----------------------------
 bool coop_eligible(const ci_layout* L);         // layout + lane count served by the cooperative kernel
 size_t coop_tape_floats(const ci_layout* L);    // [warps][T][32], lanes padded to 8
+extern int g_coop_mma;                          // regression passes of the cooperative kernel on the tensor cores (ci_set_option)
 void coop_set_option(int tpl, long max_lanes);  // tuning hook behind ci_set_option
 struct LeapArgs;
 int launch_eval_coop(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,

@@ -552,6 +552,8 @@ int ci_set_option(const char* name, long value) {
     tpl = (int)value;
   } else if (!strcmp(name, "coop_max_lanes")) {
     max_lanes = value;
+  } else if (!strcmp(name, "coop_mma")) {
+    g_coop_mma = value != 0;
   } else if (!strcmp(name, "eval_rw")) {
     g_eval_rw = value != 0;
   } else if (!strcmp(name, "eval_rw_warps")) {

@@ -42,7 +42,7 @@
 //   4 sub-threads         0.179  0.225  0.295  0.297  0.476  0.512
 #define CI_COOP_TPL8_LANES 7500L    // up to here 8 sub-threads per lane, above 4
 #define CI_COOP_MAX_LANES 13000L    // one resident wave at 4 sub-threads; above: thread-per-lane kernel
-#define CI_COOP_MAX_STAGES 8        // design-matrix chunks in flight per warp (TMA stages)
+#define CI_COOP_MAX_STAGES 16       // design-matrix chunks in flight per warp (TMA stages)
 
 namespace ci {
 
@@ -315,12 +315,42 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+
+// ---- regression passes on the tensor cores (TPL = 4, the warp's 8 lanes = 8 chains of ONE series) -------------------
+// The residual pass is the product  R[chain][t] = sum_j (-beta[j][chain]) X[t][j]  and the beta_bar pass is
+// beta_bar[chain][j] = -sum_t rbar[chain][t] X[t][j]: per series an [8 x k] x [k x T] and an [8 x T] x [T x k] matrix
+// product.  mma.sync m16n8k8 (TF32 inputs, FP32 accumulation) with the CHAINS on the M axis (rows 8..15 are zero
+// padding) puts every operand where this kernel already keeps it: thread (lane lw, sub-thread sub) is fragment
+// position (groupID = lw, threadID_in_group = sub), so the A fragments are the thread's OWN -beta slices (pass 1) /
+// OWN rbar row entries (pass 4) and the C fragment of pass 1 is two consecutive residuals of its OWN lane -- no
+// transposition anywhere.  FP32 accuracy comes from the 3xTF32 split (a = hi + lo, both TF32: hi*hi + lo*hi + hi*lo,
+// the dropped lo*lo term is 2^-22 relative), which the parity tests hold to the same 1e-4 as the FFMA path.
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// d += A (16x8, rows 8..15 zero) * B (8x8); a0 / a2 = A[groupID][tig], A[groupID][tig + 4]; b0 / b1 = B[tig][groupID], B[tig + 4][groupID]
+__device__ __forceinline__ void mma_tf32_m8(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3_tf32_m8(float (&d)[4], uint32_t ah0, uint32_t al0, uint32_t ah2, uint32_t al2, float b0,
+                                             float b1) {
+  uint32_t bh0, bl0, bh1, bl1;
+  tf32_split(b0, bh0, bl0);
+  tf32_split(b1, bh1, bl1);
+  mma_tf32_m8(d, al0, al2, bh0, bh1);      // small terms first
+  mma_tf32_m8(d, ah0, ah2, bl0, bl1);
+  mma_tf32_m8(d, ah0, ah2, bh0, bh1);
+}
+
 // register budget: each SM sub-partition owns 16 K registers, so 96 registers = 5 warps per sub-partition = 20 per SM
 // (10k lanes at TPL = 8 are 2500 warps = 17 per SM: one resident wave); 128 registers = 16 warps per SM at TPL = 4
 template <int S, int TPL>
 __global__ void __maxnreg__(TPL == 8 ? 96 : 128)
 k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
-            float* logp, float* grad, float* __restrict__ tape, LeapArgs lf, int nst) {
+            float* logp, float* grad, float* __restrict__ tape, LeapArgs lf, int nst, int use_mma) {
   extern __shared__ __align__(16) float smem[];
   using Lane = CoopLane<S, TPL>;
   constexpr int LPW = 32 / TPL, KQM = 64 / TPL;
@@ -438,7 +468,75 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     lp0 = lps + group_sum<TPL>(lpp);
   }
 
+#ifdef CI_COOP_TIMING
+  unsigned long long tm_[6];
+#define CI_TM(i) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm_[i]))
+#else
+#define CI_TM(i)
+#endif
+  CI_TM(0);
   // ---- pass 1: residuals of every step -> shared memory -------------------------------------------------------
+  // tensor-core path: TPL = 4, one series per warp, halves of an even number of chunks (host: coop_use_mma)
+  const bool mma = (TPL == 4) && use_mma != 0;
+  if constexpr (TPL == 4) {
+   if (mma) {
+    const int KK = (k + 7) >> 3;                                       // k-steps of 8 covariates
+    // NG groups of 8 steps at a time, three accumulators per group (one per term of the split): the tensor-core
+    // instructions issue in order, so consecutive ones must not depend on each other
+    auto groups = [&](auto ng_tag, int tc, const float* __restrict__ st0) {
+      constexpr int NG = decltype(ng_tag)::value;
+      float d[NG][3][4];
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) d[g][e][0] = d[g][e][1] = d[g][e][2] = d[g][e][3] = 0.f;
+      // B[j][t]: t = 8-step column lw -> chunk tc + 2 g + (lw >> 2), position lw & 3
+      const float* __restrict__ xb_ = st0 + (lw >> 2) * stage_floats + (lw & 3);
+#pragma unroll
+      for (int kk = 0; kk < KQM / 2; ++kk) {
+        if (kk < KK) {
+          uint32_t ah0, al0, ah2, al2, bh0[NG], bl0[NG], bh1[NG], bl1[NG];
+          tf32_split(nbv[2 * kk], ah0, al0);
+          tf32_split(nbv[2 * kk + 1], ah2, al2);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            tf32_split(xb_[2 * g * stage_floats + xoff[2 * kk]], bh0[g], bl0[g]);
+            tf32_split(xb_[2 * g * stage_floats + xoff[2 * kk + 1]], bh1[g], bl1[g]);
+          }
+#pragma unroll
+          for (int g = 0; g < NG; ++g) mma_tf32_m8(d[g][0], al0, al2, bh0[g], bh1[g]);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) mma_tf32_m8(d[g][1], ah0, ah2, bl0[g], bl1[g]);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) mma_tf32_m8(d[g][2], ah0, ah2, bh0[g], bh1[g]);
+        }
+      }
+      // C[lw][2 sub], C[lw][2 sub + 1] = -X beta at steps (tc + 2 g) * 4 + 2 sub (+ 1) of this thread's own lane
+      const int tl = 2 * sub;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int tcg = tc + 2 * g;
+        const float2 yv = *reinterpret_cast<const float2*>(st0 + (2 * g + (tl >> 2)) * stage_floats + k * CI_TC + (tl & 3));
+        if (tcg + (tl >> 2) < nchunk)
+          *reinterpret_cast<float2*>(rbl + tcg * CI_TC + tl) =
+              make_float2(yv.x + ((d[g][0][0] + d[g][1][0]) + d[g][2][0]), yv.y + ((d[g][0][1] + d[g][1][1]) + d[g][2][1]));
+      }
+    };
+    for (int hb = 0; hb < nhalf; ++hb) {
+      const int hp = hb & 1;
+      x_wait_half(hp);
+      const int tce = (hb + 1) * xh < nchunk ? (hb + 1) * xh : nchunk;
+      int tc = hb * xh;
+      for (; tc + 2 < tce; tc += 4)                                    // 16 steps = chunks tc .. tc + 3
+        groups(std::integral_constant<int, 2>{}, tc, sx + (hp * xh + (tc - hb * xh)) * stage_floats);
+      for (; tc < tce; tc += 2)                                        // 8 steps = chunks tc, tc + 1
+        groups(std::integral_constant<int, 1>{}, tc, sx + (hp * xh + (tc - hb * xh)) * stage_floats);
+      __syncwarp();                                                    // the staged half is consumed
+      if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
+    }
+   }
+  }
+  if (!mma)
   for (int hb = 0; hb < nhalf; ++hb) {
    const int hp = hb & 1;
    x_wait_half(hp);
@@ -492,6 +590,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
    if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
   }
 
+  CI_TM(1);
   Lane ln(sub, R, ql, qd);
   ln.init_forward(sc[SC_M0 * N], sc[SC_P0 * N]);
   // tape [warps][T][RW]: a warp's entries of consecutive steps are contiguous, S steps = one bulk copy
@@ -536,6 +635,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   if (sub == 0)
     for (int t = T; t < nchunk * CI_TC; ++t) rbl[t] = 0.f;            // steps past T carry no adjoint
 
+  CI_TM(2);
   // ---- pass 3: reverse sweep, tape blocks stream back NRB cycles ahead ---------------------------------------
   ln.init_reverse();
   {
@@ -584,6 +684,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   const float qdb = group_sum<TPL>(ln.qdacc);
   __syncwarp();                                                       // rbar rows complete
 
+  CI_TM(3);
   // ---- pass 4: beta_bar_j = -sum_t rbar_t X_tj ---------------------------------------------------------------------
   pf2 bacc[KQM];
 #pragma unroll
@@ -593,6 +694,62 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
       x_issue_half(0, 0);
       if (nhalf > 1) x_issue_half(1, 1);
     }
+    bool done = false;
+    if constexpr (TPL == 4) {
+     if (mma) {
+      // beta_bar[chain][j] = -sum_t rbar[chain][t] X[t][j]: accumulators C[lw][2 sub (+ 1)] of the 8-covariate tile jt
+      constexpr int NJT = KQM / 2;                                     // tiles of 8 covariates (k <= 64)
+      const int JT = (k + 7) >> 3;
+      float acc4[NJT][4];
+#pragma unroll
+      for (int jt = 0; jt < NJT; ++jt) acc4[jt][0] = acc4[jt][1] = acc4[jt][2] = acc4[jt][3] = 0.f;
+      // B[t][j]: j = jt * 8 + lw (rows past k alias row 0; their accumulators are never read), t = sub / sub + 4
+      int boff[NJT];
+#pragma unroll
+      for (int jt = 0; jt < NJT; ++jt) boff[jt] = ((jt * 8 + lw) < k ? (jt * 8 + lw) : 0) * CI_TC + sub;
+      for (int hb = 0; hb < nhalf; ++hb) {
+        const int hp = hb & 1;
+        x_wait_half(hp);
+        const int tce = (hb + 1) * xh < nchunk ? (hb + 1) * xh : nchunk;
+        for (int tc = hb * xh; tc < tce; tc += 2) {                    // 8 steps = chunks tc, tc + 1
+          const float* __restrict__ st0 = sx + (hp * xh + (tc - hb * xh)) * stage_floats;
+          const bool two = tc + 1 < nchunk;                            // a ragged last group has one chunk only
+          uint32_t ah0, al0, ah2, al2, bh0[NJT], bl0[NJT], bh1[NJT], bl1[NJT];
+          tf32_split(rbl[tc * CI_TC + sub], ah0, al0);
+          tf32_split(two ? rbl[tc * CI_TC + 4 + sub] : 0.f, ah2, al2);
+#pragma unroll
+          for (int jt = 0; jt < NJT; ++jt) {
+            if (jt < JT) {
+              tf32_split(st0[boff[jt]], bh0[jt], bl0[jt]);
+              tf32_split(two ? st0[stage_floats + boff[jt]] : 0.f, bh1[jt], bl1[jt]);
+            }
+          }
+          // term-major order: consecutive tensor-core instructions belong to different covariate tiles
+#pragma unroll
+          for (int jt = 0; jt < NJT; ++jt)
+            if (jt < JT) mma_tf32_m8(acc4[jt], al0, al2, bh0[jt], bh1[jt]);
+#pragma unroll
+          for (int jt = 0; jt < NJT; ++jt)
+            if (jt < JT) mma_tf32_m8(acc4[jt], ah0, ah2, bl0[jt], bl1[jt]);
+#pragma unroll
+          for (int jt = 0; jt < NJT; ++jt)
+            if (jt < JT) mma_tf32_m8(acc4[jt], ah0, ah2, bh0[jt], bh1[jt]);
+        }
+        __syncwarp();
+        if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
+      }
+      // C[lw][jt * 8 + 2 sub (+ 1)] -> the (sub + 4 q) ownership of the epilogue, through the lane's slice of region U
+      float* ex = sx + lw * 64;                                        // [8 lanes][64] floats (the stages are consumed)
+#pragma unroll
+      for (int jt = 0; jt < NJT; ++jt)
+        *reinterpret_cast<float2*>(ex + jt * 8 + 2 * sub) = make_float2(acc4[jt][0], acc4[jt][1]);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < KQM; ++q) bacc[q] = mk2(ex[sub + TPL * q], 0.f);
+      done = true;
+     }
+    }
+    if (!done)
     for (int hb = 0; hb < nhalf; ++hb) {
       const int hp = hb & 1;
       x_wait_half(hp);
@@ -618,6 +775,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     }
   }
 
+  CI_TM(4);
   // ---- VJP through the parameter transforms + priors; leapfrog kick / drift on the fresh component -----------
   // every scalar of u that more than one sub-thread reads is read BEFORE any sub-thread may drift it
   const float u0 = ub[0], u1 = ub[B];
@@ -694,10 +852,17 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     }
     if (valid) logp[b] = ll + lp0;
   }
+#ifdef CI_COOP_TIMING
+  CI_TM(5);
+  if (tid == 0 && (blockIdx.x % CI_COOP_TIMING) == 0)
+    { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); printf("blk %d sm %u start %llu p1 %llu fwd %llu rev %llu p4 %llu epi %llu\n", blockIdx.x, smid, tm_[0] % 100000000ull, tm_[1] - tm_[0], tm_[2] - tm_[1], tm_[3] - tm_[2],
+           tm_[4] - tm_[3], tm_[5] - tm_[4]); }
+#endif
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
 static int g_coop_tpl = -1;             // sub-threads per lane: 8, 4; 0 disables the cooperative kernel; -1 = by lane count
+int g_coop_mma = 1;                     // ci_set_option("coop_mma", 0 / 1): regression passes on FFMA2 / on the tensor cores
 static long g_coop_max_lanes = -1;      // -1 = default crossover to the thread-per-lane kernel
 
 void coop_set_option(int tpl, long max_lanes) {
@@ -710,15 +875,29 @@ static int coop_pick_tpl(long B) {
   return B <= CI_COOP_TPL8_LANES ? 8 : 4;
 }
 
-// design-matrix stages that fit beside the residual rows when the SM holds `warps` CTAs (at least 2, at most 8)
+// design-matrix stages that fit beside the residual rows when the SM holds `warps` CTAs (at least 2, at most 16).
+// The regression passes are bound by the latency of the staged stream (a warp has half its stages in flight), so a
+// grid that leaves SMs partly empty spends the free shared memory on deeper staging: warps = the CTAs an SM really gets.
 static int coop_stages(const ci_layout* L, int tpl) {
-  const int lpw = 32 / tpl, warps = tpl == 8 ? 17 : 16;
-  const long budget = (227L * 1024 - warps * 1024) / warps - (long)lpw * coop_row_floats(L->T, lpw) * 4 - 128;
+  const int lpw = 32 / tpl;
+  const long nwarps = ((long)L->N * L->G + lpw - 1) / lpw;
+  int warps = (int)((nwarps + 147) / 148);
+  const int wmax = tpl == 8 ? 17 : 16;
+  warps = warps > wmax ? wmax : (warps < 1 ? 1 : warps);
+  const long budget = (227L * 1024 - warps * 1024) / warps - (long)lpw * coop_row_floats(L->T, lpw) * 4 - 256;
   const long stage = (long)coop_series_max(L->G, lpw) * (L->k + 1) * CI_TC * 4;
   const long ring = (2 + 3 * (long)L->S) * lpw * 8 * 4;           // the stages alias the tape ring: that much is free
-  long nst = (budget > ring ? budget : ring) / stage;
+  long room = budget > ring ? budget : ring;
+  if (room > 48L * 1024) room = 48L * 1024;                         // the CTA stays far below the 96 KB it may ask for
+  long nst = room / stage;
   nst = nst < 2 ? 2 : (nst > CI_COOP_MAX_STAGES ? CI_COOP_MAX_STAGES : nst);
-  return (int)(nst & ~1L);                                          // two halves of nst / 2 chunks
+  nst &= ~1L;                                                       // two halves of nst / 2 chunks
+  if (tpl == 4 && g_coop_mma && nst >= 4) nst &= ~3L;               // tensor-core passes: halves of whole 8-step groups
+  return (int)nst;
+}
+// tensor-core regression passes: 4 sub-threads per lane, the 8 lanes of every warp are chains of ONE series
+static bool coop_use_mma(const ci_layout* L, int tpl) {
+  return g_coop_mma && tpl == 4 && L->k > 0 && coop_series_max(L->G, 8) == 1 && coop_stages(L, tpl) % 4 == 0;
 }
 static size_t coop_smem_bytes(const ci_layout* L, int tpl) {
   const int lpw = 32 / tpl;
@@ -757,7 +936,7 @@ static int launch_coop_t(const ci_layout* L, const ci_data* D, const float* d_u,
     configured = true;
   }
   kern<<<(unsigned)((B + LPW - 1) / LPW), 32, smem, st>>>(*L, D->d_X, D->d_sconst, d_u, d_logp, d_grad, tape, lf,
-                                                          coop_stages(L, TPL));
+                                                          coop_stages(L, TPL), coop_use_mma(L, TPL) ? 1 : 0);
   return CI_OK;
 }
 
