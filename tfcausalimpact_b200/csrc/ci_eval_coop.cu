@@ -325,8 +325,15 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
 // OWN rbar row entries (pass 4) and the C fragment of pass 1 is two consecutive residuals of its OWN lane -- no
 // transposition anywhere.  FP32 accuracy comes from the 3xTF32 split (a = hi + lo, both TF32: hi*hi + lo*hi + hi*lo,
 // the dropped lo*lo term is 2^-22 relative), which the parity tests hold to the same 1e-4 as the FFMA path.
+// Measured: HMMA.1688.F32.TF32 issues every 8 cycles per scheduler with 21 cycles latency on B200
+// (scripts/microbench/hmma_tf32_rate.cu) = 4x the multiply-add rate of FFMA2, 1.3x after the three-way split.  The
+// staged stream is not what the passes wait for: their mbarrier waits add up to 1.3 us of 83 us, and a bulk L2 prefetch
+// of the whole design block ahead of each pass changed nothing (0.2915 -> 0.2938 ms at 10,000 lanes; removed).
+// hi = x truncated to TF32 (the tensor core reads the upper 19 bits of an operand), lo = x - hi exactly (13 significant
+// bits, of which the tensor core keeps 11): two instructions.  (cvt.rna.tf32.f32 has no hardware form on sm_100a -- it
+// compiled to a six-instruction integer sequence per value and made the split cost more than the FFMA2 it replaced.)
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // d += A (16x8, rows 8..15 zero) * B (8x8); a0 / a2 = A[groupID][tig], A[groupID][tig + 4]; b0 / b1 = B[tig][groupID], B[tig + 4][groupID]
@@ -401,9 +408,20 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     for (int i = 0; i < cnt; ++i)
       bulk_copy_in(sx_u32 + (uint32_t)((p * xh + i) * stage_floats) * 4u, xsrc + (long)(tc0 + i) * xcs, xbytes, bar);
   };
+#ifdef CI_COOP_TIMING
+  unsigned long long xwait_ = 0;
+#endif
   auto x_wait_half = [&](int p) {
+#ifdef CI_COOP_TIMING
+    unsigned long long w0_, w1_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0_));
+#endif
     mbar_wait(bar0 + 8u * (uint32_t)p, (xpar >> p) & 1u);
     xpar ^= 1u << p;
+#ifdef CI_COOP_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1_));
+    xwait_ += w1_ - w0_;
+#endif
   };
   if (tid == 0) {
 #pragma unroll
@@ -477,7 +495,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
   CI_TM(0);
   // ---- pass 1: residuals of every step -> shared memory -------------------------------------------------------
   // tensor-core path: TPL = 4, one series per warp, halves of an even number of chunks (host: coop_use_mma)
-  const bool mma = (TPL == 4) && use_mma != 0;
+  const bool mma = (TPL == 4) && (use_mma & 1) != 0;
   if constexpr (TPL == 4) {
    if (mma) {
     const int KK = (k + 7) >> 3;                                       // k-steps of 8 covariates
@@ -855,7 +873,7 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
 #ifdef CI_COOP_TIMING
   CI_TM(5);
   if (tid == 0 && (blockIdx.x % CI_COOP_TIMING) == 0)
-    { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); printf("blk %d sm %u start %llu p1 %llu fwd %llu rev %llu p4 %llu epi %llu\n", blockIdx.x, smid, tm_[0] % 100000000ull, tm_[1] - tm_[0], tm_[2] - tm_[1], tm_[3] - tm_[2],
+    { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); printf("blk %d sm %u start %llu xwait(p1+p4) %llu p1 %llu fwd %llu rev %llu p4 %llu epi %llu\n", blockIdx.x, smid, tm_[0] % 100000000ull, xwait_, tm_[1] - tm_[0], tm_[2] - tm_[1], tm_[3] - tm_[2],
            tm_[4] - tm_[3], tm_[5] - tm_[4]); }
 #endif
 }
