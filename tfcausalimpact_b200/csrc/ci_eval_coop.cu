@@ -35,12 +35,16 @@
 #include "ci_xstage.cuh"
 #include "ci_kalman_eff.cuh"
 
-// lane counts served by the cooperative kernel (measured crossovers, scripts/ab_coop.py; B200, k = 50, S = 7)
-// eval ms at lanes =      1000   5000   10000  11800  15000  20000     (gpurun_out/ab_coop7_k50.jsonl)
-//   thread per lane       0.446  0.468  0.499  0.505  0.502  0.521
-//   8 sub-threads         0.132  0.216  0.324  0.394  0.460  0.585
-//   4 sub-threads         0.179  0.225  0.295  0.297  0.476  0.512
-#define CI_COOP_TPL8_LANES 7500L    // up to here 8 sub-threads per lane, above 4
+// lane counts served by the cooperative kernel (measured crossovers, scripts/ab_coop.py; B200, k = 50, S = 7, 8 chains)
+// eval ms at lanes =          1000   2000   3000   4000   5000   8000   10000  11800  15000   (profiles/r2_coop_ab_k50.jsonl)
+//   thread per lane           0.447  0.445  0.446  0.394  0.475  0.432  0.499  0.506  0.502
+//   8 sub-threads             0.126  0.127  0.159  0.161  0.208  0.266  0.325  0.381  0.460
+//   4 sub-threads, FFMA2      0.169  0.171  0.172  0.195  0.213  0.218  0.286  0.295  0.487
+//   4 sub-threads, tensor c.  0.148  0.148  0.150  0.173  0.193  0.197  0.273  0.283  0.487
+// The steps are scheduler granularity: 592 schedulers x 2 warps x 8 lanes = 9,472 lanes at 4 sub-threads (10,000 lanes
+// put a third warp on 66 schedulers: +39 % time for +25 % lanes), 592 x 2 x 4 = 4,736 lanes at 8 sub-threads.
+#define CI_COOP_TPL8_LANES 4700L        // up to here 8 sub-threads per lane (tensor-core passes available above)
+#define CI_COOP_TPL8_LANES_FFMA 6000L   // ... when the warp's lanes span several series (FFMA2 passes at 4 sub-threads)
 #define CI_COOP_MAX_LANES 13000L    // one resident wave at 4 sub-threads; above: thread-per-lane kernel
 #define CI_COOP_MAX_STAGES 16       // design-matrix chunks in flight per warp (TMA stages)
 
@@ -824,22 +828,90 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     gsn = pn.sp;
     sq_gsv = sqrtf(gsv);
     const float Gs = gsn * sq_gsv * CI_WEIGHTS_PRIOR_SCALE;
-#pragma unroll
-    for (int q = 0; q < KQM; ++q) {
-      const int j = sub + TPL * q;
-      if (j < k) {
-        const float a = ub[(long)(4 + j) * B], bq = ub[(long)(4 + k + j) * B], wn = ub[(long)(4 + 2 * k + j) * B];
-        const float bb = -(bacc[q].x + bacc[q].y);
-        const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(bq);
-        const float lsv = pa.sp, lsn = pb.sp;
-        const float sq = sqrtf(lsv);
-        const float ilsv = rcp(lsv);
-        const float l = lsn * sq;
-        dG = fmaf(bb, wn * l, dG);
-        const float dl = bb * wn * Gs;
-        emit(4 + 2 * k + j, bb * l * Gs - wn);
-        emit(4 + k + j, (dl * sq - lsn) * pb.sig + pb.nsig);
-        emit(4 + j, (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig);
+    if constexpr (TPL == 4) {
+      // Three phases, so that the strided global loads of a phase are all in flight together: grad / the leapfrog arrays
+      // may alias u as far as the compiler knows (lf.uu IS u), and a load-compute-store loop per covariate serialised
+      // one memory round trip per covariate (the epilogue took 19-35 us of a 280 us evaluation at 10,000 lanes).
+      // (A) the raw parameters of every covariate of this sub-thread
+      float pa_[KQM], pb_[KQM], pw_[KQM];
+  #pragma unroll
+      for (int q = 0; q < KQM; ++q) {
+        const int j = (sub + TPL * q) < k ? (sub + TPL * q) : 0;       // past k: a valid address, the value is not used
+        pa_[q] = ub[(long)(4 + j) * B];
+        pb_[q] = ub[(long)(4 + k + j) * B];
+        pw_[q] = ub[(long)(4 + 2 * k + j) * B];
+      }
+      // (B) the three gradient components per covariate (in place of the raw parameters)
+  #pragma unroll
+      for (int q = 0; q < KQM; ++q) {
+        if (sub + TPL * q < k) {
+          const float wn = pw_[q];
+          const float bb = -(bacc[q].x + bacc[q].y);
+          const SoftplusPack pa = softplus_pack(pa_[q]), pb = softplus_pack(pb_[q]);
+          const float lsv = pa.sp, lsn = pb.sp;
+          const float sq = sqrtf(lsv);
+          const float ilsv = rcp(lsv);
+          const float l = lsn * sq;
+          dG = fmaf(bb, wn * l, dG);
+          const float dl = bb * wn * Gs;
+          pw_[q] = bb * l * Gs - wn;
+          pb_[q] = (dl * sq - lsn) * pb.sig + pb.nsig;
+          pa_[q] = (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig;
+        }
+      }
+      // (C) stores + leapfrog, one parameter block at a time, loads of a half block batched ahead of its stores
+      auto emit_block = [&](int p0, const float (&gv)[KQM]) {
+  #pragma unroll
+        for (int h0 = 0; h0 < KQM; h0 += KQM / 2) {
+          float e_[KQM / 2], pp_[KQM / 2], uu_[KQM / 2];
+          if (leap) {
+  #pragma unroll
+            for (int i = 0; i < KQM / 2; ++i) {
+              const int j = (sub + TPL * (h0 + i)) < k ? (sub + TPL * (h0 + i)) : 0;
+              const long o = (long)(p0 + j) * B + b;
+              e_[i] = lf.step0[o];
+              pp_[i] = lf.pp[o];
+              uu_[i] = lf.last ? 0.f : lf.uu[o];
+            }
+          }
+  #pragma unroll
+          for (int i = 0; i < KQM / 2; ++i) {
+            const int j = sub + TPL * (h0 + i);
+            if (j < k && valid) {
+              const long o = (long)(p0 + j) * B + b;
+              const float g1 = gv[h0 + i];
+              grad[o] = g1;
+              if (leap) {
+                const float eps = e_[i] * lfac;
+                const float ph = fmaf(lc * eps, g1, pp_[i]);
+                lf.pp[o] = ph;
+                if (!lf.last) lf.uu[o] = fmaf(eps, ph, uu_[i]);
+              }
+            }
+          }
+        }
+      };
+      emit_block(4 + 2 * k, pw_);
+      emit_block(4 + k, pb_);
+      emit_block(4, pa_);
+    } else {   // 8 sub-threads (96-register budget): the per-covariate loop measured faster (0.126 vs 0.130 ms at 1,000 lanes)
+  #pragma unroll
+      for (int q = 0; q < KQM; ++q) {
+        const int j = sub + TPL * q;
+        if (j < k) {
+          const float a = ub[(long)(4 + j) * B], bq = ub[(long)(4 + k + j) * B], wn = ub[(long)(4 + 2 * k + j) * B];
+          const float bb = -(bacc[q].x + bacc[q].y);
+          const SoftplusPack pa = softplus_pack(a), pb = softplus_pack(bq);
+          const float lsv = pa.sp, lsn = pb.sp;
+          const float sq = sqrtf(lsv);
+          const float ilsv = rcp(lsv);
+          const float l = lsn * sq;
+          dG = fmaf(bb, wn * l, dG);
+          const float dl = bb * wn * Gs;
+          emit(4 + 2 * k + j, bb * l * Gs - wn);
+          emit(4 + k + j, (dl * sq - lsn) * pb.sig + pb.nsig);
+          emit(4 + j, (dl * lsn * 0.5f * sq * ilsv + ilsv * (0.5f * ilsv - 1.5f)) * pa.sig + pa.nsig);
+        }
       }
     }
     dG = group_sum<TPL>(dG);
@@ -888,9 +960,11 @@ void coop_set_option(int tpl, long max_lanes) {
   g_coop_max_lanes = max_lanes;
 }
 
-static int coop_pick_tpl(long B) {
+static int coop_pick_tpl(const ci_layout* L) {
   if (g_coop_tpl >= 0) return g_coop_tpl;
-  return B <= CI_COOP_TPL8_LANES ? 8 : 4;
+  const long B = (long)L->N * L->G;
+  const bool tc = g_coop_mma && L->k > 0 && coop_series_max(L->G, 8) == 1;   // tensor-core passes at 4 sub-threads
+  return B <= (tc ? CI_COOP_TPL8_LANES : CI_COOP_TPL8_LANES_FFMA) ? 8 : 4;
 }
 
 // design-matrix stages that fit beside the residual rows when the SM holds `warps` CTAs (at least 2, at most 16).
@@ -930,7 +1004,7 @@ bool coop_eligible(const ci_layout* L) {
   const long B = (long)L->N * L->G;
   const long lim = g_coop_max_lanes >= 0 ? g_coop_max_lanes : CI_COOP_MAX_LANES;
   if (B > lim) return false;
-  return coop_smem_bytes(L, coop_pick_tpl(B)) <= 96 * 1024;
+  return coop_smem_bytes(L, coop_pick_tpl(L)) <= 96 * 1024;
 }
 
 size_t coop_tape_floats(const ci_layout* L) {
@@ -974,7 +1048,7 @@ static int launch_coop_s(const ci_layout* L, const ci_data* D, const float* d_u,
 
 int launch_eval_coop(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                      float* tape, cudaStream_t st, const LeapArgs& lf) {
-  const int tpl = coop_pick_tpl((long)L->N * L->G);
+  const int tpl = coop_pick_tpl(L);
   const int rc = tpl == 8 ? launch_coop_s<8>(L, D, d_u, d_logp, d_grad, tape, st, lf)
                           : launch_coop_s<4>(L, D, d_u, d_logp, d_grad, tape, st, lf);
   if (rc) return rc;
