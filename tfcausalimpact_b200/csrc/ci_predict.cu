@@ -351,7 +351,6 @@ k_onestep_sample_tiled(int N, int G, int T, int nsamp, int slab, uint64_t seed, 
   const uint32_t sid0 = (uint32_t)row0;
   const uint32_t sms_u32 = smem_u32(sms);
   const int nfull = nloc & ~3;
-  const size_t TQ = (size_t)T * (ONESTEP_NT / 8);
   const int niter = (T - 1) / 32 + 2;                            // runs of a sample: a partial head, whole lines, a tail
   for (int m = 0; m < niter; ++m) {
     const int tb = 32 * m;                                       // block of steps staged in this iteration
@@ -377,34 +376,36 @@ k_onestep_sample_tiled(int N, int G, int T, int nsamp, int slab, uint64_t seed, 
     __syncthreads();
     if (tb + 32 < T) fetch(tb + 32);
     const int tl = tb - 32 + lane;                               // + shift = this lane's step
-    auto emit = [&](unsigned e16, float z, float* prow) {
+    // branch-free: the staged row (t & 63) exists for every t, only the store is predicated on 0 <= t < T;
+    // 32-bit element index inside the slab (slab * T < 2^32, checked by the host), one wide multiply-add per store
+    auto emit = [&](unsigned e16, float z, uint32_t row_idx) {
       const int t = tl + (int)(e16 >> 8);
-      if ((unsigned)t < (unsigned)T) {
-        float2 v;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                     : "=f"(v.x), "=f"(v.y)
-                     : "r"(sms_u32 + (uint32_t)((t & 63) * GP + (int)(e16 & 0xffu)) * 8u));
-        prow[t] = fmaf(v.y, z, v.x);
-      }
+      float2 v;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                   : "=f"(v.x), "=f"(v.y)
+                   : "r"(sms_u32 + (uint32_t)((t & 63) * GP + (int)(e16 & 0xffu)) * 8u));
+      const float val = fmaf(v.y, z, v.x);
+      if ((unsigned)t < (unsigned)T) out0[row_idx + (uint32_t)t] = val;
     };
-    float* p0 = out0 + (size_t)(warp * 4) * T;
+    const uint32_t uT = (uint32_t)T;
+    uint32_t r0 = (uint32_t)(warp * 4) * uT;
     int q = warp * 4;
     for (; q < nfull; q += ONESTEP_NT / 8) {
       // counter = (first sample of the quad, iteration, lane): four normals, one per sample of the quad
       const f32x4 z = philox_normal4_fast(sid0 + (uint32_t)q, (uint32_t)(tb + lane), 1u, TAG_ONESTEP, seed);
       const uint2 jj = *reinterpret_cast<const uint2*>(sdraw + q);
-      emit(jj.x & 0xffffu, z.x, p0);
-      emit(jj.x >> 16, z.y, p0 + T);
-      emit(jj.y & 0xffffu, z.z, p0 + 2 * (size_t)T);
-      emit(jj.y >> 16, z.w, p0 + 3 * (size_t)T);
-      p0 += TQ;
+      emit(jj.x & 0xffffu, z.x, r0);
+      emit(jj.x >> 16, z.y, r0 + uT);
+      emit(jj.y & 0xffffu, z.z, r0 + 2u * uT);
+      emit(jj.y >> 16, z.w, r0 + 3u * uT);
+      r0 += (uint32_t)(ONESTEP_NT / 8) * uT;
     }
     if (q < nloc) {                                              // the slab's last, partial quad
       const f32x4 z = philox_normal4_fast(sid0 + (uint32_t)q, (uint32_t)(tb + lane), 1u, TAG_ONESTEP, seed);
       const uint2 jj = *reinterpret_cast<const uint2*>(sdraw + q);
-      emit(jj.x & 0xffffu, z.x, p0);
-      if (q + 1 < nloc) emit(jj.x >> 16, z.y, p0 + T);
-      if (q + 2 < nloc) emit(jj.y & 0xffffu, z.z, p0 + 2 * (size_t)T);
+      emit(jj.x & 0xffffu, z.x, r0);
+      if (q + 1 < nloc) emit(jj.x >> 16, z.y, r0 + uT);
+      if (q + 2 < nloc) emit(jj.y & 0xffffu, z.z, r0 + 2u * uT);
     }
   }
 }
@@ -621,7 +622,7 @@ int ci_onestep_sample(const ci_layout* L, const float* d_pred_mean, const float*
   CI_CHECK_ARG(nsamp >= 0 && (nsamp == 0 || d_pre_sims), "d_pre_sims is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (nsamp > 0) {
-    if (g_onestep_tiled && L->G <= ONESTEP_TILED_MAX_G && L->N <= 65535 * 16) {
+    if (g_onestep_tiled && L->G <= ONESTEP_TILED_MAX_G && (long)L->T * 2112 < (1L << 32)) {   // 32-bit index inside a slab
       // slab of samples per CTA: a multiple of 4, at most 2048, small enough that the grid covers ~4 CTAs per SM
       int nsl = (int)((4L * 148 + L->N - 1) / L->N);
       if (nsl < (nsamp + 2047) / 2048) nsl = (nsamp + 2047) / 2048;
