@@ -96,6 +96,10 @@ GEN_CASES = [
     (O.FLAG_LLT | O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL, 12, 1, 2, 64, 0.0, 2, 2),
     (O.FLAG_OBS_LOGNORMAL, 1, 1, 2, 45, 0.0, 3, 1),                                      # sparse + LogNormal noise prior
     (O.FLAG_LLT, 3, 1, 40, 40, 0.0, 1, 2),
+    # generic priors WITHOUT a trend slope and a large latent, few lanes: the register-resident 4-warp kernel (ci_eval_rw.cu)
+    (O.FLAG_DENSE_REG | O.FLAG_OBS_LOGNORMAL | O.FLAG_LEVEL_LOGNORMAL, 12, 1, 3, 64, 0.05, 2, 2),
+    (O.FLAG_OBS_LOGNORMAL, 20, 2, 0, 50, 0.0, 2, 1),
+    (O.FLAG_DENSE_REG, 52, 1, 2, 110, 0.0, 1, 2),
 ]
 
 
