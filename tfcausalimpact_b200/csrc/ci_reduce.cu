@@ -124,33 +124,42 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
   }
 }
 
-template <int NW>
-__device__ __forceinline__ uint32_t warp_select(const uint32_t (&plane)[NW][32], int rank) {
-  uint32_t mask[NW];
+// MSB-first radix select of NR order statistics AT ONCE: per bit one AND + popc per plane word and ONE warp reduction
+// (redux.sync, a single instruction for integers) per rank; the NR chains are independent, so their dependent
+// popc -> redux -> compare -> mask steps interleave (the four ranks np.percentile needs were four sequential 32-step
+// chains of five shuffles each before: 4.84 ms for 2000 series x 1000 draws x 395 steps).
+template <int NW, int NR>
+__device__ __forceinline__ void warp_select_n(const uint32_t (&plane)[NW][32], const int (&rank)[NR], uint32_t (&key)[NR]) {
+  uint32_t mask[NR][NW];
+  int remaining[NR];
 #pragma unroll
-  for (int w = 0; w < NW; ++w) mask[w] = 0xFFFFFFFFu;
-  uint32_t prefix = 0u;
-  int remaining = rank;
+  for (int r = 0; r < NR; ++r) {
+    key[r] = 0u;
+    remaining[r] = rank[r];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mask[r][w] = 0xFFFFFFFFu;
+  }
 #pragma unroll
   for (int b = 31; b >= 0; --b) {
-    uint32_t z[NW];
-    int cz = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      z[w] = mask[w] & ~plane[w][31 - b];   // candidates with bit b clear
-      cz += __popc(z[w]);
+    for (int r = 0; r < NR; ++r) {
+      uint32_t z[NW];
+      unsigned cz = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        z[w] = mask[r][w] & ~plane[w][31 - b];   // candidates with bit b clear
+        cz += __popc(z[w]);
+      }
+      cz = __reduce_add_sync(0xffffffffu, cz);
+      const bool zero = remaining[r] < (int)cz;   // the wanted key has bit b clear
+      if (!zero) {
+        remaining[r] -= (int)cz;
+        key[r] |= (1u << b);
+      }
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mask[r][w] = zero ? z[w] : (mask[r][w] & plane[w][31 - b]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cz += __shfl_xor_sync(0xffffffffu, cz, o);
-    const bool zero = remaining < cz;       // the wanted key has bit b clear
-    if (!zero) {
-      remaining -= cz;
-      prefix |= (1u << b);
-    }
-#pragma unroll
-    for (int w = 0; w < NW; ++w) mask[w] = zero ? z[w] : (mask[w] & plane[w][31 - b]);
   }
-  return prefix;
 }
 
 template <int NW>
@@ -178,10 +187,11 @@ k_col_quantiles_sel(int W, int nsamp, QPos q, const float* __restrict__ mat, flo
     }
     transpose32(plane[w]);
   }
-  const float lo0 = from_sortable(warp_select<NW>(plane, q.lo0));
-  const float lo1 = from_sortable(warp_select<NW>(plane, q.lo1));
-  const float hi0 = from_sortable(warp_select<NW>(plane, q.hi0));
-  const float hi1 = from_sortable(warp_select<NW>(plane, q.hi1));
+  const int ranks[4] = {q.lo0, q.lo1, q.hi0, q.hi1};
+  uint32_t keys[4];
+  warp_select_n<NW, 4>(plane, ranks, keys);
+  const float lo0 = from_sortable(keys[0]), lo1 = from_sortable(keys[1]);
+  const float hi0 = from_sortable(keys[2]), hi1 = from_sortable(keys[3]);
   if (lane == 0) {
     out[((long)n * 2 + 0) * W + w0 + c] = lerp_np(lo0, lo1, q.flo);
     out[((long)n * 2 + 1) * W + w0 + c] = lerp_np(hi0, hi1, q.fhi);
