@@ -101,6 +101,13 @@ struct LeapArgs;
 int launch_eval_coop(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad,
                      float* tape, cudaStream_t stream, const LeapArgs& lf);
 
+// ---- warp-specialised thread-per-lane evaluation for mid-size batches, ci_eval_ws.cu ----------------------------
+extern int g_eval_ws;                           // ci_set_option("eval_ws", 0 / 1)
+extern long g_ws_max_lanes;                     // ci_set_option("eval_ws_max_lanes", lanes; -1 = default)
+bool ws_eligible(const ci_layout* L);
+int launch_eval_ws(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad, float* tape,
+                   cudaStream_t stream, const LeapArgs& lf);
+
 // Per-evaluation scratch: only the filter tape leaves the evaluation kernel (see ci_eval.cu).
 struct EvalWs {
   float* tape;   // [T][S+1][B] (g_0..g_{S-1}, v), or warp-blocked [T][B/32][S+1][32] (effects path)

@@ -24,6 +24,7 @@
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
 #include "ci_xstage.cuh"
+#include "ci_leap.cuh"
 
 namespace ci {
 
@@ -75,36 +76,6 @@ __host__ __device__ inline int staged_series_max(int G) {
 // workload run as ONE wave (the run time of a lane is fixed by its T sequential steps).
 // EFF selects the seasonal-effects formulation (ci_kalman_eff.cuh; season_duration == 1) with the
 // warp-blocked tape [T][warps][S+1][32] whose per-step addresses are one pointer bump + immediates.
-__device__ __forceinline__ void leap_epilogue(const LeapArgs& lf, int P, long B, long b,
-                                              const float* __restrict__ grad) {
-  if (lf.pp == nullptr) return;
-  float* __restrict__ pp = lf.pp + b;
-  float* __restrict__ uu = lf.uu + b;
-  const float* __restrict__ st = lf.step0 + b;
-  const float* __restrict__ gr = grad + b;
-  const float fac = expf(lf.logfac[b]);
-  const float c = lf.last ? 0.5f : 1.0f;
-  constexpr int U = 8;   // 8 parameters per round: 32 independent loads in flight
-  for (int i0 = 0; i0 < P; i0 += U) {
-    float e[U], g[U], p[U], x[U];
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const long o = (long)(i0 + q < P ? i0 + q : P - 1) * B;
-      e[q] = st[o]; g[q] = gr[o]; p[q] = pp[o]; x[q] = uu[o];
-    }
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      if (i0 + q < P) {
-        const long o = (long)(i0 + q) * B;
-        const float eps = e[q] * fac;
-        const float ph = fmaf(c * eps, g[q], p[q]);
-        pp[o] = ph;
-        if (!lf.last) uu[o] = fmaf(eps, ph, x[q]);
-      }
-    }
-  }
-}
-
 __global__ void k_leap(LeapArgs lf, int P, long B, const float* __restrict__ grad) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) leap_epilogue(lf, P, B, b, grad);
@@ -361,6 +332,7 @@ int launch_eval(const ci_layout* L, const ci_data* D, const float* d_u, float* d
     return CI_OK;
   }
   if (coop_eligible(L)) return launch_eval_coop(L, D, d_u, d_logp, d_grad, ws.tape, st, lf);
+  if (ws_eligible(L)) return launch_eval_ws(L, D, d_u, d_logp, d_grad, ws.tape, st, lf);
   const bool eff = L->r == 1 && L->S >= 2 && L->S <= CI_MAX_EFF_S;
   const bool small = eff && (long)L->N * L->G <= CI_SMALL_LANES;
 #define CI_EFF_S(S_) (S_ >= 2 && S_ <= CI_MAX_EFF_S)
@@ -552,6 +524,10 @@ int ci_set_option(const char* name, long value) {
     tpl = (int)value;
   } else if (!strcmp(name, "coop_max_lanes")) {
     max_lanes = value;
+  } else if (!strcmp(name, "eval_ws")) {
+    g_eval_ws = value != 0;
+  } else if (!strcmp(name, "eval_ws_max_lanes")) {
+    g_ws_max_lanes = value;
   } else if (!strcmp(name, "coop_mma")) {
     g_coop_mma = value != 0;
   } else if (!strcmp(name, "eval_rw")) {
