@@ -10,6 +10,7 @@ k = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 T, Tf, S = 365, 30, 7
 lib = nt.lib()
+if os.environ.get('AB_WSMAX'): nt.check(lib.ci_set_option(b'eval_ws_max_lanes', ctypes.c_long(int(os.environ['AB_WSMAX']))), 'opt')
 if os.environ.get('AB_NOCOOP'): nt.check(lib.ci_set_option(b'coop_threads_per_lane', ctypes.c_long(0)), 'opt')
 def opt(name, v): nt.check(lib.ci_set_option(name, ctypes.c_long(v)), 'ci_set_option')
 def time_eval(db, u, it=20):

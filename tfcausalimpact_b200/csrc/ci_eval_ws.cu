@@ -1,4 +1,4 @@
-// K1-K3 for MID-SIZE batches (above the lane-cooperative kernel's one-wave limit, below a full machine: ~13k .. 30k
+// K1-K3 for MID-SIZE batches (above the lane-cooperative kernel's one-wave limit, below a full machine: ~13k .. 28k
 // lanes -- the named configs[3] split at 4 GPUs): thread-per-lane evaluation with the regression taken OFF the
 // dependent Kalman chain by warp specialisation.
 //
@@ -12,12 +12,15 @@
 //     accumulation), from TMA-staged design chunks it double-buffers itself.
 // They meet through a two-slot shared-memory exchange ([2][32][4] residuals forward, rbar backward) behind mbarriers
 // (full / empty per slot): no CTA-wide barrier inside the sweeps, the helper is never more than two chunks ahead.
-// With 13k-30k lanes the SMs have idle schedulers, so the helper warps cost nothing the main warps could have used.
-// Measured (scripts/ab_ws.py, k = 50, 8 chains, ms per evaluation, single-warp kernel -> this one): 15,000 lanes
-// 0.508 -> 0.379, 20,000 0.519 -> 0.435, 24,000 0.522 -> 0.454, 28,000 0.521 -> 0.440, 30,000 0.586 -> 0.510; above that
-// the helper warps compete for issue slots (35,200: 0.527 -> 0.563, 40,000: 0.607 -> 0.667) and the single-warp kernel
-// stays.  One CTA alone: 0.447 -> 0.317 ms; the main warp waits 2 % of its time on the exchange, its own chain (tape
-// reads from L2 inside the reverse step: 885 cycles per reverse step, 496 per forward step) is what is left.
+// With 13k-28k lanes the SMs have idle schedulers, so the helper warps cost nothing the main warps could have used.
+// The helper also stages the TAPE for the reverse sweep: a step's entry of the warp is one contiguous (S + 1) x 128-byte
+// run, which it bulk-copies (TMA) into a two-chunk shared-memory ring while the main warp works on the previous chunk,
+// so the reverse step starts from shared memory instead of an L2 round trip (885 -> ~600 cycles per reverse step).
+// Measured (scripts/ab_ws.py, k = 50, 8 chains, ms per evaluation, single-warp kernel -> this one; profiles/
+// r2_ws_ab_k50.jsonl): one CTA alone 0.446 -> 0.263; 15,000 lanes 0.509 -> 0.296; 20,000 0.521 -> 0.352; 28,000
+// 0.522 -> 0.355 (without the tape staging: 0.379 / 0.435 / 0.440).  Beyond one wave at 6 CTAs per SM (28,416 lanes) a
+// 128-register build gave 32,000: 0.522 -> 0.504, 35,200: 0.526 -> 0.566, 40,000: 0.607 -> 0.717 (helper warps then
+// compete with main warps for issue slots): the single-warp kernel stays there.
 // Same math and tests as the other evaluation kernels (tests/test_ws_gpu.py).
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
@@ -55,8 +58,9 @@ __device__ __forceinline__ void ws_tma(uint32_t dst, const void* src, uint32_t b
                : "memory");
 }
 
-// barrier slots (8 bytes each): forward xfull[2] rfull[2] rempty[2], reverse xfull[2] rfull[2] rempty[2]
-enum { WS_XF = 0, WS_RF = 2, WS_RE = 4, WS_REV = 6, WS_NBAR = 12 };
+// barrier slots (8 bytes each): forward xfull[2] rfull[2] rempty[2], reverse xfull[2] rfull[2] rempty[2], then
+// tape-ready (forward tape complete) and tape-full[2] (a chunk's tape entries staged for the reverse steps)
+enum { WS_XF = 0, WS_RF = 2, WS_RE = 4, WS_REV = 6, WS_TR = 12, WS_TF = 13, WS_NBAR = 15 };
 
 // MINB = resident CTAs per SM the register budget must allow: 6 -> 170 registers (one wave up to 28,416 lanes), 8 -> 128
 // (37,888 lanes).  The main warp's filter steps want ~164 registers (ci_eval.cu, SMALL instantiation).
@@ -79,7 +83,9 @@ k_eval_ws(ci_layout L, const float* __restrict__ XY, const float* __restrict__ s
   float* sr = smem + k * 32;                              // [2][32][4] exchange slots
   float* sx = sr + 2 * 32 * 4;                            // [2][smax][stride] staged design chunks
   const int stage_floats = smax * stride;
-  const uint32_t bar0 = smem_u32(sx + 2 * stage_floats);
+  constexpr int TE = (S + 1) * 32;                        // floats of one step's tape entry of the warp
+  float* sring = sx + 2 * stage_floats;                   // [2][CI_TC][TE] tape entries staged for the reverse steps
+  const uint32_t bar0 = smem_u32(sring + 2 * CI_TC * TE);
   const int n_lo = (int)(bw0 / L.G);
   const long b_last = (bw0 + 31 < B ? bw0 + 31 : B - 1);
   const int ns = (int)(b_last / L.G) - n_lo + 1;
@@ -133,16 +139,21 @@ k_eval_ws(ci_layout L, const float* __restrict__ XY, const float* __restrict__ s
     for (int i = 0; i < ES + 1; ++i) Ln.st.m[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < EState<ES>::NP; ++i) Ln.st.P[i] = 0.f;
-    Ln.tp -= tstep;                                       // entry of step T - 1
+    // the forward tape (generic-proxy stores of all 32 lanes) must be visible to the helper's bulk (async-proxy) loads
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) ws_arrive(bar0 + 8u * WS_TR);
     c = (T - 1) % ES;
     for (int tc = nchunk - 1, it = 0; tc >= 0; --tc, ++it) {
       const int slot = it & 1;
       float rb[4] = {0.f, 0.f, 0.f, 0.f};
       const int nstep = (T - tc * CI_TC) < CI_TC ? (T - tc * CI_TC) : CI_TC;
+      ws_wait(bar0 + 8u * (WS_TF + slot), (uint32_t)(it >> 1) & 1u);   // the chunk's tape entries are in shared memory
 #pragma unroll
       for (int i = CI_TC - 1; i >= 0; --i) {
         if (i < nstep) {
-          rb[i] = Ln.template disp_bwd<0>(c, tc * CI_TC + i >= CI_TAPE_AHEAD);
+          Ln.tp = sring + (slot * CI_TC + i) * TE + lane;
+          rb[i] = Ln.template disp_bwd<0>(c, false);
           c = (c == 0) ? ES - 1 : c - 1;
         }
       }
@@ -205,9 +216,33 @@ k_eval_ws(ci_layout L, const float* __restrict__ XY, const float* __restrict__ s
       if (nchunk > 1)
         ws_tma(sx_u32 + (uint32_t)stage_floats * 4u, xsrc + (long)(nchunk - 2) * xcs, xbytes, bar0 + 8u * (WS_REV + WS_XF + 1));
     }
+    // tape entries of a chunk (one contiguous (S + 1) x 128-byte run per step in the warp-blocked layout) -> ring slot
+    const float* wtape = tape + (bw0 >> 5) * TE;
+    const long tstep_g = (long)((B + 31) / 32) * TE;
+    const uint32_t ring_u32 = smem_u32(sring);
+    auto tape_issue = [&](int tc, int slot) {                                     // lane 0
+      const int nstep = (T - tc * CI_TC) < CI_TC ? (T - tc * CI_TC) : CI_TC;
+      const uint32_t bar = bar0 + 8u * (WS_TF + slot);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(nstep * TE) * 4u) : "memory");
+      for (int i = 0; i < nstep; ++i)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ring_u32 + (uint32_t)((slot * CI_TC + i) * TE) * 4u),
+                     "l"(wtape + (long)(tc * CI_TC + i) * tstep_g), "r"((uint32_t)TE * 4u), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+      ws_wait(bar0 + 8u * WS_TR, 0u);                      // the main warp has finished (and fenced) the forward tape
+      asm volatile("fence.proxy.async;" ::: "memory");
+      tape_issue(nchunk - 1, 0);
+      if (nchunk > 1) tape_issue(nchunk - 2, 1);
+    }
     for (int tc = nchunk - 1, it = 0; tc >= 0; --tc, ++it) {
       const int slot = it & 1;
       ws_wait(bar0 + 8u * (WS_REV + WS_RF + slot), (uint32_t)(it >> 1) & 1u);
+      if (lane == 0 && tc - 2 >= 0) {                      // the main warp is done with the slot's tape entries too
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tape_issue(tc - 2, slot);
+      }
       ws_wait(bar0 + 8u * (WS_REV + WS_XF + slot), (uint32_t)(it >> 1) & 1u);
       const float4 rb = *reinterpret_cast<const float4*>(sr + (slot * 32 + lane) * 4);
       const pf2 n01 = mk2(-rb.x, -rb.y), n23 = mk2(-rb.z, -rb.w);
@@ -258,11 +293,12 @@ k_eval_ws(ci_layout L, const float* __restrict__ XY, const float* __restrict__ s
 // ---- host side ------------------------------------------------------------------------------------------------
 int g_eval_ws = 1;                       // ci_set_option("eval_ws", 0 / 1)
 #define CI_WS_LANES_6 (148L * 6 * 32)    // one wave at 6 CTAs (= 6 main warps) per SM: 28,416 lanes, 170 registers
-#define CI_WS_MAX_LANES 30400L           // measured crossover to the single-warp kernel (one wave at 8 CTAs per SM would be 37,888)
+#define CI_WS_MAX_LANES CI_WS_LANES_6     // beyond one wave at 6 CTAs per SM the 128-register build wins little or loses (below)
 long g_ws_max_lanes = -1;                // ci_set_option("eval_ws_max_lanes"): -1 = default
 
 static size_t ws_smem_bytes(const ci_layout* L) {
-  return ((size_t)L->k * 32 + 2 * 32 * 4 + 2 * (size_t)ws_series_max(L->G) * (L->k + 1) * CI_TC) * 4 + WS_NBAR * 8 + 16;
+  return ((size_t)L->k * 32 + 2 * 32 * 4 + 2 * (size_t)ws_series_max(L->G) * (L->k + 1) * CI_TC +
+          2 * CI_TC * (size_t)(L->S + 1) * 32) * 4 + WS_NBAR * 8 + 16;
 }
 
 bool ws_eligible(const ci_layout* L) {
