@@ -19,8 +19,8 @@
 // Measured (scripts/ab_ws.py, k = 50, 8 chains, ms per evaluation, single-warp kernel -> this one; profiles/
 // r2_ws_ab_k50.jsonl): one CTA alone 0.446 -> 0.263; 15,000 lanes 0.509 -> 0.296; 20,000 0.521 -> 0.352; 28,000
 // 0.522 -> 0.355 (without the tape staging: 0.379 / 0.435 / 0.440).  Beyond one wave at 6 CTAs per SM (28,416 lanes) a
-// 128-register build gave 32,000: 0.522 -> 0.504, 35,200: 0.526 -> 0.566, 40,000: 0.607 -> 0.717 (helper warps then
-// compete with main warps for issue slots): the single-warp kernel stays there.
+// 128-register build gave 32,000: 0.522 -> 0.504, 35,200: 0.526 -> 0.566, 40,000: 0.607 -> 0.717 and a 96-register build
+// 40,000: 0.607 -> 0.663 (helper warps then compete with main warps for issue slots): the single-warp kernel stays there.
 // Same math and tests as the other evaluation kernels (tests/test_ws_gpu.py).
 #include "ci_abi_common.cuh"
 #include "ci_eval_lane.cuh"
@@ -62,8 +62,9 @@ __device__ __forceinline__ void ws_tma(uint32_t dst, const void* src, uint32_t b
 // tape-ready (forward tape complete) and tape-full[2] (a chunk's tape entries staged for the reverse steps)
 enum { WS_XF = 0, WS_RF = 2, WS_RE = 4, WS_REV = 6, WS_TR = 12, WS_TF = 13, WS_NBAR = 15 };
 
-// MINB = resident CTAs per SM the register budget must allow: 6 -> 170 registers (one wave up to 28,416 lanes), 8 -> 128
-// (37,888 lanes).  The main warp's filter steps want ~164 registers (ci_eval.cu, SMALL instantiation).
+// MINB = resident CTAs per SM the register budget must allow: 6 -> up to 170 registers (one wave up to 28,416 lanes); the
+// main warp's filter steps take 148.  Builds for 8 / 9 CTAs per SM (128 / 96 registers) were measured and lost to the
+// single-warp kernel above 28k lanes (header).
 template <int S, int MINB>
 __global__ void __launch_bounds__(64, MINB)
 k_eval_ws(ci_layout L, const float* __restrict__ XY, const float* __restrict__ sconst, const float* u,
@@ -306,7 +307,7 @@ bool ws_eligible(const ci_layout* L) {
   if (L->r != 1 || L->S < 2 || L->S > CI_MAX_EFF_S || L->G < 4 || L->k < 4) return false;
   const long B = (long)L->N * L->G;
   if (B > (g_ws_max_lanes >= 0 ? g_ws_max_lanes : CI_WS_MAX_LANES)) return false;
-  return ws_smem_bytes(L) * 8 <= (size_t)220 * 1024;
+  return ws_smem_bytes(L) * 6 <= (size_t)220 * 1024;
 }
 
 template <int S, int MINB>
@@ -329,9 +330,7 @@ static int launch_ws_t(const ci_layout* L, const ci_data* D, const float* d_u, f
 int launch_eval_ws(const ci_layout* L, const ci_data* D, const float* d_u, float* d_logp, float* d_grad, float* tape,
                    cudaStream_t st, const LeapArgs& lf) {
   int rc = CI_OK;
-  const bool wide = (long)L->N * L->G <= CI_WS_LANES_6;
-#define CI_WS_CASE(S_) case S_: rc = wide ? launch_ws_t<S_, 6>(L, D, d_u, d_logp, d_grad, tape, st, lf) \
-                                          : launch_ws_t<S_, 8>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;
+#define CI_WS_CASE(S_) case S_: rc = launch_ws_t<S_, 6>(L, D, d_u, d_logp, d_grad, tape, st, lf); break;
   switch (L->S) {
     CI_WS_CASE(2) CI_WS_CASE(3) CI_WS_CASE(4) CI_WS_CASE(5) CI_WS_CASE(6) CI_WS_CASE(7)
     default: return fail(CI_ERR_UNSUPPORTED, "warp-specialised evaluation needs 2 <= nseasons <= 7");
