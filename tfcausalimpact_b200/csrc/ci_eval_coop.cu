@@ -356,6 +356,12 @@ __device__ __forceinline__ void mma3_tf32_m8(float (&d)[4], uint32_t ah0, uint32
   mma_tf32_m8(d, ah0, ah2, bh0, bh1);
 }
 
+// (A two-warp build of the 4-sub-thread kernel -- regression passes in a helper warp, concurrent with the sweeps: the
+// residual pass ahead of the filter, the beta_bar pass trailing the reverse sweep in descending time order, 112
+// registers, nine 64-thread CTAs per SM -- was built and measured: one CTA alone 0.148 -> 0.120 ms, but 5,000 lanes
+// 0.195 -> 0.218, 8,000 lanes 0.198 -> 0.283, 10,000 lanes 0.272 -> 0.367 ms: with two main warps per scheduler the
+// helper warps take issue slots from the sweeps, which is where the time is.  Not kept; the thread-per-lane kernel,
+// whose lanes are whole threads, does profit from a helper warp between 13k and 28k lanes: ci_eval_ws.cu.)
 // register budget: each SM sub-partition owns 16 K registers, so 96 registers = 5 warps per sub-partition = 20 per SM
 // (10k lanes at TPL = 8 are 2500 warps = 17 per SM: one resident wave); 128 registers = 16 warps per SM at TPL = 4
 template <int S, int TPL>
