@@ -27,7 +27,9 @@ def _case(N, T, Tf, nsamp, seed, mask_frac=0.0):
 
 @pytest.mark.parametrize('N,T,Tf,nsamp,alpha,mask_frac', [
     (3, 40, 12, 1000, 0.05, 0.0), (2, 17, 9, 100, 0.1, 0.3), (1, 70, 30, 1000, 0.05, 0.0),
-    (2, 10, 5, 1500, 0.2, 0.2), (1, 12, 7, 3000, 0.05, 0.0), (1, 9, 4, 7, 0.5, 0.0)])
+    (2, 10, 5, 1500, 0.2, 0.2), (1, 12, 7, 3000, 0.05, 0.0), (1, 9, 4, 7, 0.5, 0.0),
+    (2, 20, 130, 300, 0.05, 0.2),      # post period longer than the shared-memory running-sum tile (direct kernel)
+    (3, 15, 96, 257, 0.05, 0.1)])      # ... exactly at its limit, a partial last 128-row tile
 def test_reductions_match_numpy(N, T, Tf, nsamp, alpha, mask_frac):
     from tfcausalimpact_b200.engine import DeviceBatch
     y_pre, y_post, pre_sims, pre_mean, post_sims, post_mean = _case(N, T, Tf, nsamp, N * 7 + T, mask_frac)

@@ -39,6 +39,7 @@ WS_CASES = [
     (6, 8, 45, 0.3, 5, 4),
     (4, 6, 30, 0.0, 40, 8),      # ten warps
     (7, 64, 33, 0.1, 9, 32),     # one series per warp
+    (7, 100, 40, 0.0, 3, 8),     # more covariates than the cooperative kernel takes: this kernel serves small batches too
 ]
 
 
