@@ -966,11 +966,23 @@ void coop_set_option(int tpl, long max_lanes) {
   g_coop_max_lanes = max_lanes;
 }
 
+static size_t coop_smem_bytes(const ci_layout* L, int tpl);
+// one resident wave? (CTAs per SM the grid needs) x (shared memory of a CTA + the 1 KB the driver reserves) must fit an SM
+static bool coop_one_wave(const ci_layout* L, int tpl) {
+  const int lpw = 32 / tpl;
+  const long nwarps = ((long)L->N * L->G + lpw - 1) / lpw;
+  const long per_sm = (nwarps + 147) / 148;
+  return per_sm <= (tpl == 8 ? 20 : 16) && per_sm * (long)(coop_smem_bytes(L, tpl) + 1024) <= 227L * 1024;
+}
 static int coop_pick_tpl(const ci_layout* L) {
   if (g_coop_tpl >= 0) return g_coop_tpl;
   const long B = (long)L->N * L->G;
   const bool tc = g_coop_mma && L->k > 0 && coop_series_max(L->G, 8) == 1;   // tensor-core passes at 4 sub-threads
-  return B <= (tc ? CI_COOP_TPL8_LANES : CI_COOP_TPL8_LANES_FFMA) ? 8 : 4;
+  if (B <= (tc ? CI_COOP_TPL8_LANES : CI_COOP_TPL8_LANES_FFMA)) return 8;
+  // 4 sub-threads stage 8 lanes' series per chunk: with one lane per series (the reference's default settings) that is
+  // 8 x 16 (k + 1) bytes per stage and a second wave from 9,472 lanes on (measured, k = 50, one lane per series, 10,000
+  // lanes: 0.598 ms against 0.464 ms at 8 sub-threads; 8,000 lanes: 0.308 against 0.338)
+  return coop_one_wave(L, 4) ? 4 : 8;
 }
 
 // design-matrix stages that fit beside the residual rows when the SM holds `warps` CTAs (at least 2, at most 16).
