@@ -117,9 +117,11 @@ int ci_kalman_logp_grad(const ci_layout* L, const ci_data* D, const float* d_u, 
  *   "coop_threads_per_lane"  -1 (default: chosen by lane count), 8, 4, or 0 = never use the lane-cooperative kernel
  *   "coop_max_lanes"         largest N * G served by it (-1 = default: the measured crossover)
  *   "coop_mma"               1 (default) regression passes of the lane-cooperative kernel on the tensor cores (3xTF32), 0 = FFMA2
- *   "eval_ws"                1 (default) mid-size batches (above the cooperative kernel, up to 42,624 lanes) run on the warp-specialised
+ *   "eval_ws"                1 (default) mid-size batches (above the cooperative kernel, up to 28,416 lanes) run on the warp-specialised
  *                            kernel (csrc/ci_eval_ws.cu: filter steps and regression in two warps per 32 lanes)
- *   "eval_rw"                1 (default) few-lane / large-latent evaluations run on the register-resident 4-warp kernel
+ *   "eval_ws_max_lanes"      largest N * G served by it (-1 = default)
+ *   "eval_rw"                1 (default) few-lane / large-latent evaluations run on the register-resident kernel (csrc/ci_eval_rw.cu)
+ *   "eval_rw_warps"          4 (default) or 8 warps per lane in that kernel
  *   "filter_fused"           1 (default) ci_filter_predict runs as one fused kernel, 0 = the three-kernel path
  *   "onestep_tiled"          1 (default) ci_onestep_sample stages each series' predictive moments in shared memory
  * The lane-cooperative kernel (csrc/ci_eval_coop.cu) serves default-model layouts with 2 <= nseasons <= 7,
