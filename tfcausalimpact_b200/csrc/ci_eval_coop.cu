@@ -346,6 +346,13 @@ __device__ __forceinline__ void mma_tf32_m8(float (&d)[4], uint32_t a0, uint32_t
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
+// d += A (16x8) * B (8x8), all four A registers: a0 / a1 = A[groupID (+ 8)][tig], a2 / a3 = A[groupID (+ 8)][tig + 4]
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void mma3_tf32_m8(float (&d)[4], uint32_t ah0, uint32_t al0, uint32_t ah2, uint32_t al2, float b0,
                                              float b1) {
   uint32_t bh0, bl0, bh1, bl1;
@@ -550,13 +557,48 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
               make_float2(yv.x + ((d[g][0][0] + d[g][1][0]) + d[g][2][0]), yv.y + ((d[g][0][1] + d[g][1][1]) + d[g][2][1]));
       }
     };
+    // 16 steps at a time with the STEPS on the M axis (no padding rows: half the tensor-core instructions of two
+    // 8-step groups): A[t][j] = X (rows t = lw, lw + 8), B[j][chain] = the thread's own -beta slices, and
+    // C[t][chain] lands in ANOTHER lane's row -- conflict-free scattered stores (bank = 8 sub + lw)
+    auto group16 = [&](int tc, const float* __restrict__ st0) {
+      float d[3][4];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) d[e][0] = d[e][1] = d[e][2] = d[e][3] = 0.f;
+      const float* __restrict__ xa = st0 + (lw >> 2) * stage_floats + (lw & 3);   // step lw; step lw + 8 is two chunks on
+      const int s2 = 2 * stage_floats;
+#pragma unroll
+      for (int kk = 0; kk < KQM / 2; ++kk) {
+        if (kk < KK) {
+          uint32_t bh0, bl0, bh1, bl1, ah[4], al[4];
+          tf32_split(nbv[2 * kk], bh0, bl0);
+          tf32_split(nbv[2 * kk + 1], bh1, bl1);
+          tf32_split(xa[xoff[2 * kk]], ah[0], al[0]);
+          tf32_split(xa[s2 + xoff[2 * kk]], ah[1], al[1]);
+          tf32_split(xa[xoff[2 * kk + 1]], ah[2], al[2]);
+          tf32_split(xa[s2 + xoff[2 * kk + 1]], ah[3], al[3]);
+          mma_tf32(d[0], al[0], al[1], al[2], al[3], bh0, bh1);
+          mma_tf32(d[1], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+          mma_tf32(d[2], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+        }
+      }
+      const float y0 = xa[k * CI_TC], y1 = xa[s2 + k * CI_TC];          // centred series at steps lw, lw + 8
+      float* r0 = smem + (2 * sub) * RS + tc * CI_TC + lw;              // row of chain 2 sub, step lw of the group
+      if (tc + (lw >> 2) < nchunk) {
+        r0[0] = y0 + ((d[0][0] + d[1][0]) + d[2][0]);
+        r0[RS] = y0 + ((d[0][1] + d[1][1]) + d[2][1]);
+      }
+      if (tc + 2 + (lw >> 2) < nchunk) {
+        r0[8] = y1 + ((d[0][2] + d[1][2]) + d[2][2]);
+        r0[RS + 8] = y1 + ((d[0][3] + d[1][3]) + d[2][3]);
+      }
+    };
     for (int hb = 0; hb < nhalf; ++hb) {
       const int hp = hb & 1;
       x_wait_half(hp);
       const int tce = (hb + 1) * xh < nchunk ? (hb + 1) * xh : nchunk;
       int tc = hb * xh;
-      for (; tc + 2 < tce; tc += 4)                                    // 16 steps = chunks tc .. tc + 3
-        groups(std::integral_constant<int, 2>{}, tc, sx + (hp * xh + (tc - hb * xh)) * stage_floats);
+      for (; tc + 3 < tce; tc += 4)                                    // 16 steps = chunks tc .. tc + 3
+        group16(tc, sx + (hp * xh + (tc - hb * xh)) * stage_floats);
       for (; tc < tce; tc += 2)                                        // 8 steps = chunks tc, tc + 1
         groups(std::integral_constant<int, 1>{}, tc, sx + (hp * xh + (tc - hb * xh)) * stage_floats);
       __syncwarp();                                                    // the staged half is consumed
@@ -725,16 +767,22 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
     bool done = false;
     if constexpr (TPL == 4) {
      if (mma) {
-      // beta_bar[chain][j] = -sum_t rbar[chain][t] X[t][j]: accumulators C[lw][2 sub (+ 1)] of the 8-covariate tile jt
-      constexpr int NJT = KQM / 2;                                     // tiles of 8 covariates (k <= 64)
-      const int JT = (k + 7) >> 3;
+      // beta_bar[j][chain] = -sum_t X[t][j] rbar[chain][t] with the COVARIATES on the M axis (16 per tile, no padding
+      // rows): A[j][t] = X (j = jt * 16 + lw, + 8; t = sub, sub + 4), B[t][chain] = the thread's own rbar row entries,
+      // accumulators C[j][chain 2 sub (+ 1)] -- 3 x ceil(k / 16) tensor-core instructions per 8 steps instead of
+      // 3 x ceil(k / 8)
+      constexpr int NJT = KQM / 4;                                     // tiles of 16 covariates (k <= 64)
+      const int JT = (k + 15) >> 4;
       float acc4[NJT][4];
 #pragma unroll
       for (int jt = 0; jt < NJT; ++jt) acc4[jt][0] = acc4[jt][1] = acc4[jt][2] = acc4[jt][3] = 0.f;
-      // B[t][j]: j = jt * 8 + lw (rows past k alias row 0; their accumulators are never read), t = sub / sub + 4
-      int boff[NJT];
+      // rows past k alias row 0 (finite values; their accumulators are never read)
+      int aoff0[NJT], aoff1[NJT];
 #pragma unroll
-      for (int jt = 0; jt < NJT; ++jt) boff[jt] = ((jt * 8 + lw) < k ? (jt * 8 + lw) : 0) * CI_TC + sub;
+      for (int jt = 0; jt < NJT; ++jt) {
+        aoff0[jt] = ((jt * 16 + lw) < k ? (jt * 16 + lw) : 0) * CI_TC + sub;
+        aoff1[jt] = ((jt * 16 + 8 + lw) < k ? (jt * 16 + 8 + lw) : 0) * CI_TC + sub;
+      }
       for (int hb = 0; hb < nhalf; ++hb) {
         const int hp = hb & 1;
         x_wait_half(hp);
@@ -742,38 +790,45 @@ k_eval_coop(ci_layout L, const float* __restrict__ XY, const float* __restrict__
         for (int tc = hb * xh; tc < tce; tc += 2) {                    // 8 steps = chunks tc, tc + 1
           const float* __restrict__ st0 = sx + (hp * xh + (tc - hb * xh)) * stage_floats;
           const bool two = tc + 1 < nchunk;                            // a ragged last group has one chunk only
-          uint32_t ah0, al0, ah2, al2, bh0[NJT], bl0[NJT], bh1[NJT], bl1[NJT];
-          tf32_split(rbl[tc * CI_TC + sub], ah0, al0);
-          tf32_split(two ? rbl[tc * CI_TC + 4 + sub] : 0.f, ah2, al2);
+          uint32_t bh0, bl0, bh1, bl1, ah[NJT][4], al[NJT][4];
+          tf32_split(rbl[tc * CI_TC + sub], bh0, bl0);
+          tf32_split(two ? rbl[tc * CI_TC + 4 + sub] : 0.f, bh1, bl1);
 #pragma unroll
           for (int jt = 0; jt < NJT; ++jt) {
             if (jt < JT) {
-              tf32_split(st0[boff[jt]], bh0[jt], bl0[jt]);
-              tf32_split(two ? st0[stage_floats + boff[jt]] : 0.f, bh1[jt], bl1[jt]);
+              tf32_split(st0[aoff0[jt]], ah[jt][0], al[jt][0]);
+              tf32_split(st0[aoff1[jt]], ah[jt][1], al[jt][1]);
+              tf32_split(two ? st0[stage_floats + aoff0[jt]] : 0.f, ah[jt][2], al[jt][2]);
+              tf32_split(two ? st0[stage_floats + aoff1[jt]] : 0.f, ah[jt][3], al[jt][3]);
             }
           }
           // term-major order: consecutive tensor-core instructions belong to different covariate tiles
 #pragma unroll
           for (int jt = 0; jt < NJT; ++jt)
-            if (jt < JT) mma_tf32_m8(acc4[jt], al0, al2, bh0[jt], bh1[jt]);
+            if (jt < JT) mma_tf32(acc4[jt], al[jt][0], al[jt][1], al[jt][2], al[jt][3], bh0, bh1);
 #pragma unroll
           for (int jt = 0; jt < NJT; ++jt)
-            if (jt < JT) mma_tf32_m8(acc4[jt], ah0, ah2, bl0[jt], bl1[jt]);
+            if (jt < JT) mma_tf32(acc4[jt], ah[jt][0], ah[jt][1], ah[jt][2], ah[jt][3], bl0, bl1);
 #pragma unroll
           for (int jt = 0; jt < NJT; ++jt)
-            if (jt < JT) mma_tf32_m8(acc4[jt], ah0, ah2, bh0[jt], bh1[jt]);
+            if (jt < JT) mma_tf32(acc4[jt], ah[jt][0], ah[jt][1], ah[jt][2], ah[jt][3], bh0, bh1);
         }
         __syncwarp();
         if (tid == 0 && hb + 2 < nhalf) x_issue_half(hb + 2, hp);
       }
-      // C[lw][jt * 8 + 2 sub (+ 1)] -> the (sub + 4 q) ownership of the epilogue, through the lane's slice of region U
-      float* ex = sx + lw * 64;                                        // [8 lanes][64] floats (the stages are consumed)
+      // C[jt * 16 + lw (+ 8)][chain 2 sub (+ 1)] -> the [lane][sub + 4 q] ownership of the epilogue, through region U
+      float* ex = sx;                                                  // [8 lanes][64] floats (the stages are consumed)
 #pragma unroll
-      for (int jt = 0; jt < NJT; ++jt)
-        *reinterpret_cast<float2*>(ex + jt * 8 + 2 * sub) = make_float2(acc4[jt][0], acc4[jt][1]);
+      for (int jt = 0; jt < NJT; ++jt) {
+        const int j0 = jt * 16 + lw;
+        ex[(2 * sub) * 64 + j0] = acc4[jt][0];
+        ex[(2 * sub + 1) * 64 + j0] = acc4[jt][1];
+        ex[(2 * sub) * 64 + j0 + 8] = acc4[jt][2];
+        ex[(2 * sub + 1) * 64 + j0 + 8] = acc4[jt][3];
+      }
       __syncwarp();
 #pragma unroll
-      for (int q = 0; q < KQM; ++q) bacc[q] = mk2(ex[sub + TPL * q], 0.f);
+      for (int q = 0; q < KQM; ++q) bacc[q] = mk2(ex[lw * 64 + sub + TPL * q], 0.f);
       done = true;
      }
     }
