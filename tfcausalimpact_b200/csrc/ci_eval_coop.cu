@@ -321,14 +321,18 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
 
 
 // ---- regression passes on the tensor cores (TPL = 4, the warp's 8 lanes = 8 chains of ONE series) -------------------
-// The residual pass is the product  R[chain][t] = sum_j (-beta[j][chain]) X[t][j]  and the beta_bar pass is
-// beta_bar[chain][j] = -sum_t rbar[chain][t] X[t][j]: per series an [8 x k] x [k x T] and an [8 x T] x [T x k] matrix
-// product.  mma.sync m16n8k8 (TF32 inputs, FP32 accumulation) with the CHAINS on the M axis (rows 8..15 are zero
-// padding) puts every operand where this kernel already keeps it: thread (lane lw, sub-thread sub) is fragment
-// position (groupID = lw, threadID_in_group = sub), so the A fragments are the thread's OWN -beta slices (pass 1) /
-// OWN rbar row entries (pass 4) and the C fragment of pass 1 is two consecutive residuals of its OWN lane -- no
-// transposition anywhere.  FP32 accuracy comes from the 3xTF32 split (a = hi + lo, both TF32: hi*hi + lo*hi + hi*lo,
-// the dropped lo*lo term is 2^-22 relative), which the parity tests hold to the same 1e-4 as the FFMA path.
+// The residual pass is the product  R[t][chain] = sum_j X[t][j] (-beta[j][chain])  and the beta_bar pass is
+// beta_bar[j][chain] = -sum_t X[t][j] rbar[chain][t]: per series a [T x k] x [k x 8] and a [k x T] x [T x 8] matrix
+// product.  mma.sync m16n8k8 (TF32 inputs, FP32 accumulation) with the 8 CHAINS on the N axis and full 16-row tiles on
+// M (16 steps / 16 covariates): thread (lane lw, sub-thread sub) is fragment position (groupID = lw, threadID_in_group
+// = sub), so the B fragments are the thread's OWN -beta slices (pass 1) / OWN rbar row entries (pass 4); the A
+// fragments are scalar shared-memory loads of the staged design chunk; the C fragment of pass 1 goes to the rows of
+// chains 2 sub, 2 sub + 1 (conflict-free scattered stores), that of pass 4 through a small exchange to the epilogue's
+// ownership.  (A first version put the chains on M -- rows 8..15 zero padding, every fragment the thread's own data --
+// and needed twice the tensor-core instructions: 0.272 against 0.261 ms at 10,000 lanes.)  Ragged ends (fewer than four
+// chunks left in a half) still use that 8-row form.  FP32 accuracy comes from the 3xTF32 split (a = hi + lo, both
+// TF32: hi*hi + lo*hi + hi*lo, the dropped lo*lo term is 2^-22 relative), which the parity tests hold to the same 1e-4
+// as the FFMA path.
 // Measured: HMMA.1688.F32.TF32 issues every 8 cycles per scheduler with 21 cycles latency on B200
 // (scripts/microbench/hmma_tf32_rate.cu) = 4x the multiply-add rate of FFMA2, 1.3x after the three-way split.  The
 // staged stream is not what the passes wait for: their mbarrier waits add up to 1.3 us of 83 us, and a bulk L2 prefetch
