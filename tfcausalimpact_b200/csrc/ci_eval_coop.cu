@@ -43,6 +43,9 @@
 //   4 sub-threads, tensor c.  0.148  0.148  0.150  0.173  0.193  0.197  0.273  0.283  0.487
 // The steps are scheduler granularity: 592 schedulers x 2 warps x 8 lanes = 9,472 lanes at 4 sub-threads (10,000 lanes
 // put a third warp on 66 schedulers: +39 % time for +25 % lanes), 592 x 2 x 4 = 4,736 lanes at 8 sub-threads.
+// The step is sharp -- 9,472 lanes 0.200 ms, 9,600 lanes 0.258 ms -- because the kernel ends with its slowest scheduler.
+// (Running the overflow past 9,472 lanes as a second launch of 8-sub-thread warps on a side stream, so that the third
+// warp leaves its scheduler half way through, was measured: 10,000 lanes 0.259 -> 0.262 ms.  Not kept.)
 #define CI_COOP_TPL8_LANES 4700L        // up to here 8 sub-threads per lane (tensor-core passes available above)
 #define CI_COOP_TPL8_LANES_FFMA 6000L   // ... when the warp's lanes span several series (FFMA2 passes at 4 sub-threads)
 #define CI_COOP_MAX_LANES 13000L    // one resident wave at 4 sub-threads; above: thread-per-lane kernel
