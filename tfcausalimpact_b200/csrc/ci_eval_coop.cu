@@ -36,17 +36,18 @@
 #include "ci_kalman_eff.cuh"
 
 // lane counts served by the cooperative kernel (measured crossovers, scripts/ab_coop.py; B200, k = 50, S = 7, 8 chains)
-// eval ms at lanes =          1000   2000   3000   4000   5000   8000   10000  11800  15000   (profiles/r2_coop_ab_k50.jsonl)
-//   thread per lane           0.447  0.445  0.446  0.394  0.475  0.432  0.499  0.506  0.502
-//   8 sub-threads             0.126  0.127  0.159  0.161  0.208  0.266  0.325  0.381  0.460
-//   4 sub-threads, FFMA2      0.169  0.171  0.172  0.195  0.213  0.218  0.286  0.295  0.487
-//   4 sub-threads, tensor c.  0.148  0.148  0.150  0.173  0.193  0.197  0.273  0.283  0.487
+// eval ms at lanes =          1000   2000   3000   4000   5000   8000   9472   10000  11800  15000  (profiles/r2_coop_ab_k50.jsonl)
+//   thread per lane           0.447  0.445  0.446  0.394  0.475  0.432  --     0.499  0.506  0.502   (single-warp kernel)
+//   thread per lane + helper  0.262  0.272  0.269  0.285  0.290  0.293  0.295  0.295  0.295  0.295   (ci_eval_ws.cu)
+//   8 sub-threads             0.126  0.128  0.159  0.161  0.209  0.266  0.267  0.324  0.394  0.461
+//   4 sub-threads, FFMA2      0.173  0.174  0.173  0.193  0.217  0.222  0.235  0.288  0.295  0.481
+//   4 sub-threads, tensor c.  0.142  0.143  0.142  0.161  0.187  0.191  0.204  0.261  0.261  0.445
 // The steps are scheduler granularity: 592 schedulers x 2 warps x 8 lanes = 9,472 lanes at 4 sub-threads (10,000 lanes
 // put a third warp on 66 schedulers: +39 % time for +25 % lanes), 592 x 2 x 4 = 4,736 lanes at 8 sub-threads.
 // The step is sharp -- 9,472 lanes 0.200 ms, 9,600 lanes 0.258 ms -- because the kernel ends with its slowest scheduler.
 // (Running the overflow past 9,472 lanes as a second launch of 8-sub-thread warps on a side stream, so that the third
 // warp leaves its scheduler half way through, was measured: 10,000 lanes 0.259 -> 0.262 ms.  Not kept.)
-#define CI_COOP_TPL8_LANES 4700L        // up to here 8 sub-threads per lane (tensor-core passes available above)
+#define CI_COOP_TPL8_LANES 2500L        // up to here 8 sub-threads per lane (tensor-core passes available above)
 #define CI_COOP_TPL8_LANES_FFMA 6000L   // ... when the warp's lanes span several series (FFMA2 passes at 4 sub-threads)
 #define CI_COOP_MAX_LANES 13000L    // one resident wave at 4 sub-threads; above: thread-per-lane kernel
 #define CI_COOP_MAX_STAGES 16       // design-matrix chunks in flight per warp (TMA stages)
