@@ -21,6 +21,7 @@
 // and the kernel can choose between TMA-staged shared memory and direct global loads.
 // Math: SURVEY.md Appendix A.2-A.5.
 #pragma once
+#include <type_traits>
 #include "ci_core.cuh"
 #include "ci_kalman.cuh"
 #include "ci_params.cuh"
@@ -33,6 +34,26 @@ namespace ci {
 struct f4 {
   float x, y, z, w;
 };
+
+// Tape reads: every entry is read exactly once, after an L2 prefetch CI_TAPE_AHEAD steps earlier -> streaming
+// (evict-first) loads, so the consumed lines leave L2 ahead of the design chunks and the tape still to come: measured
+// 0.8233 -> 0.8152 ms per evaluation and 13.21 -> 13.06 ms per HMC transition at configs[3] (scripts/ab_eval.py, three
+// rounds; the same hint on the tape STORES changed nothing and is not used).
+template <bool STREAM>
+CI_HD float tape_load(const float* p) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (STREAM) return __ldcs(p);   // ld.global.cs: the pointer must be a global address
+  else return *p;
+#else
+  return *p;
+#endif
+}
+// an X-source policy that declares `using tape_in_shared = void;` hands the reverse sweep tape entries staged in shared
+// memory (ci_eval_ws.cu): plain generic loads there
+template <class XS, class = void>
+struct tape_streams { static constexpr bool value = true; };
+template <class XS>
+struct tape_streams<XS, std::void_t<typename XS::tape_in_shared>> { static constexpr bool value = false; };
 
 CI_HD void prefetch_l2(const float* p) {
 #if defined(__CUDA_ARCH__)
@@ -356,7 +377,7 @@ struct EffLane {
     float cur[D];
 #ifndef CI_NO_TAPE
 #pragma unroll
-    for (int q = 0; q < D; ++q) cur[q] = tp[q * TQ];
+    for (int q = 0; q < D; ++q) cur[q] = tape_load<tape_streams<XS>::value>(tp + q * TQ);
     if (far && pfoff != 0) prefetch_l2(tp + pfoff);
 #else
 #pragma unroll

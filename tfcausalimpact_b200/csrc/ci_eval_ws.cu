@@ -30,7 +30,9 @@
 
 namespace ci {
 
-struct XNone {};   // EffLane's own regression members are never instantiated here
+struct XNone {     // EffLane's own regression members are never instantiated here
+  using tape_in_shared = void;   // the reverse steps read tape entries the helper staged in shared memory
+};
 
 __host__ __device__ inline int ws_series_max(int G) {   // series a warp's 32 lanes can touch
   const int a = (32 + G - 2) / G + 1;
