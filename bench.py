@@ -337,7 +337,9 @@ def strong_records(args, rank, world, dev, dist, barrier, weak_ms_per_step):
 
 
 def cfg4_eval_record(dev, fp32_peak):
-    """configs[4] shape (100 series x 10,000 steps, nseasons=52, no covariates): the CTA-per-lane evaluation."""
+    """configs[4] shape (100 series x 10,000 steps, nseasons=52, no covariates): the few-lane / large-latent evaluation
+    (csrc/ci_eval_rw.cu).  A latency-bound kernel: its time follows the SM clock, and this record is taken at the end of a
+    long run (7.87 ms at 1965 MHz on a fresh box, ~8.1 ms here when the box sits at 1860-1930 MHz under its power cap)."""
     from tfcausalimpact_b200.engine import DeviceBatch
     N, T, Tf, S = 100, 10000, 520, 52
     y, _ = synth(N, T, Tf, 0, S, 5, dev)
