@@ -64,13 +64,18 @@ def test_logp_grad_matches_oracle(S, r, k, T, nan_frac, N, G):
     assert np.all(np.abs(g - go) <= 1e-4 * np.abs(go) + 1e-5 * gmax)
 
 
-def test_linearity_property_full_size():
+@pytest.mark.parametrize('N', [128, 512, 1250, 2500, 7200])
+def test_linearity_property_full_size(N):
     """Size-independent property at cfg4 scale: with all variance parameters fixed, dL/dr is an
     affine function of the residual series, so grad wrt weights_noncentered is affine along a
-    line in weight space (checked at three collinear points)."""
+    line in weight space (checked at three collinear points).  The series counts put the call on each evaluation
+    kernel of the default dispatch (8 chains): cooperative with 8 and with 4 sub-threads (1,024 / 4,096 / 10,000 lanes:
+    the 8-GPU share of configs[3]), warp-specialised (20,000 lanes: the 4-GPU share), thread-per-lane (57,600 lanes)."""
     from tfcausalimpact_b200.engine import DeviceBatch
-    N, G, T, Tf, k, S = 512, 8, 365, 30, 50, 7
-    y, _, X = synth_problem(N, T, Tf, k, S, 1, seed=3)
+    G, T, Tf, k, S = 8, 365, 30, 50, 7
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=(N, T)).astype(np.float32).cumsum(axis=1) * 0.1 + rng.normal(size=(N, T)).astype(np.float32)
+    X = rng.normal(size=(N, T + Tf, k)).astype(np.float32)
     db = DeviceBatch(y, X, Tf=Tf, nseasons=S)
     L = O.Layout(T, Tf, k, S, 1)
     g = torch.Generator(device='cpu').manual_seed(0)
