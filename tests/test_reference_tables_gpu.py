@@ -83,3 +83,28 @@ def test_google_vi_notebook_table_20_seeds():
     assert _within(127.92, m[3], s[3]), (m, s)
     assert _within(36.07, m[5], s[5]), (m, s)
     assert m[4] < 0.01
+
+
+def test_volks_with_regressors_r_package_table():
+    """R package on the weekly Volkswagen data with both regressors (/root/reference/notebooks/R/volks/summary.txt.txt:
+    Actual 127, Prediction 171 (5.6) [159, 182], absolute effect -44 (5.6) [-55, -33], p 0.001) -- local level + static
+    regression in both packages, different samplers and priors on the weights: a second anchor at half a posterior
+    s.d. for the prediction and 15 % for its spread, mean over 8 HMC seeds (seed-to-seed s.d. of the prediction 0.4)."""
+    from tfcausalimpact_b200 import CausalImpact
+    data = pd.read_csv(os.path.join(GOLD, 'volks_data.csv'), header=0, sep=' ', index_col='Date', parse_dates=True)
+    pre = [str(np.min(data.index.values)), '2015-09-13']
+    post = ['2015-09-20', str(np.max(data.index.values))]
+    rows = []
+    for seed in range(8):
+        ci = CausalImpact(data, pre, post, model_args={'fit_method': 'hmc', 'seed': seed})
+        sd = ci.summary_data
+        lo, hi = sd.loc['predicted_lower', 'average'], sd.loc['predicted_upper', 'average']
+        rows.append([sd.loc['actual', 'average'], sd.loc['predicted', 'average'], (hi - lo) / (2 * Z), lo, hi,
+                     sd.loc['abs_effect', 'average'], ci.p_value])
+    m = np.array(rows, dtype=np.float64).mean(axis=0)
+    assert round(m[0]) == 127
+    assert abs(m[1] - 171) < 0.5 * 5.6 + 0.5, m
+    assert abs(m[2] / 5.6 - 1.0) < 0.15, m
+    assert abs(m[3] - 159) < 3.0 and abs(m[4] - 182) < 3.0, m
+    assert abs(m[5] + 44) < 0.5 * 5.6 + 0.5, m
+    assert m[6] < 0.01
