@@ -108,3 +108,26 @@ def test_volks_with_regressors_r_package_table():
     assert abs(m[3] - 159) < 3.0 and abs(m[4] - 182) < 3.0, m
     assert abs(m[5] + 44) < 0.5 * 5.6 + 0.5, m
     assert m[6] < 0.01
+
+
+def test_basque_r_package_table():
+    """R package on the Basque-country series with one control (/root/reference/notebooks/R/basque/summary.txt.txt, data
+    notebooks/R/basque.csv copied to tests/golden: 21 yearly pre-period points, 22 post): Actual 7.9 / 173.1,
+    Prediction 8.6 (0.31) [8.1, 9.2], absolute effect -0.76 (0.31) [-1.4, -0.2], p 0.004.  Mean over 8 HMC seeds."""
+    from tfcausalimpact_b200 import CausalImpact
+    data = pd.read_csv(os.path.join(GOLD, 'basque.csv'), index_col='date', parse_dates=True)
+    rows = []
+    for seed in range(8):
+        ci = CausalImpact(data, ['1955-01-01', '1975-01-01'], ['1976-01-01', '1997-01-01'],
+                          model_args={'fit_method': 'hmc', 'seed': seed})
+        sd = ci.summary_data
+        lo, hi = sd.loc['predicted_lower', 'average'], sd.loc['predicted_upper', 'average']
+        rows.append([sd.loc['actual', 'average'], sd.loc['actual', 'cumulative'], sd.loc['predicted', 'average'],
+                     (hi - lo) / (2 * Z), lo, hi, sd.loc['abs_effect', 'average'], ci.p_value])
+    m = np.array(rows, dtype=np.float64).mean(axis=0)
+    assert round(m[0], 1) == 7.9 and abs(m[1] - 173.1) < 0.06
+    assert abs(m[2] - 8.6) < 0.5 * 0.31 + 0.05, m
+    assert abs(m[3] / 0.31 - 1.0) < 0.2, m
+    assert abs(m[4] - 8.1) < 0.25 and abs(m[5] - 9.2) < 0.25, m
+    assert abs(m[6] + 0.76) < 0.5 * 0.31 + 0.05, m
+    assert m[7] < 0.05
